@@ -1,0 +1,145 @@
+/* nerrf_b200 -- C-ABI of the B200-native NERRF AI hot path.
+ *
+ * The reference (Itz-Agasta/nerrf @ a38ae13) has NO FFI / plugin interface for this path
+ * (SURVEY.md 8b): the ai/ module it names (README.md:72-76) was never written.  The entry
+ * points below are therefore the boundary a maintainer WOULD bind from the Python `ai/`
+ * package the README names; each cites the reference interface (prose) it realises.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - every entry point returns 0 on success, <0 on error; the message is available from
+ *     nerrf_last_error() (thread-local); nothing throws across the ABI;
+ *   - device-pointer entry points are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*; NULL = default stream), allocate nothing, and own nothing: the caller owns all
+ *     inputs, outputs and workspaces;
+ *   - *_host entry points take HOST pointers (pinned for async copies), do the H2D / D2H
+ *     copies themselves and synchronise before returning; the only persistent allocations
+ *     live inside an explicit opaque session handle (create / destroy).
+ *   - all matrices row-major fp32; indices int32 (rowptr int32 or int64).
+ */
+#ifndef NERRF_B200_H
+#define NERRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERRF_ABI_VERSION 1
+
+#define NERRF_OK 0
+#define NERRF_ERR_INVALID (-1)   /* bad argument (shape, alignment, unsupported size)      */
+#define NERRF_ERR_CUDA (-2)      /* a CUDA runtime call / kernel launch failed              */
+#define NERRF_ERR_NODEVICE (-3)  /* no sm_100 device                                        */
+#define NERRF_ERR_WORKSPACE (-4) /* workspace too small                                     */
+
+/* algo selector for the GraphSAGE-T layer */
+#define NERRF_SAGE_ALGO_AUTO 0
+#define NERRF_SAGE_ALGO_FFMA 1   /* fused gather+aggregate -> fp32 CUDA-core GEMM           */
+#define NERRF_SAGE_ALGO_UMMA 2   /* fused gather+aggregate -> tcgen05 bf16x3 GEMM (TMEM)    */
+
+typedef void* nerrf_stream_t;    /* cudaStream_t */
+
+int nerrf_abi_version(void);
+const char* nerrf_last_error(void);
+/* sm count / compute capability of the current device; NERRF_ERR_NODEVICE if none. */
+int nerrf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ GraphSAGE-T (rows a1-a3)
+ * Replaces: ai/models/GraphSAGE-T.py `GraphSAGE_T.forward` (README.md:73, ROADMAP.md:127;
+ * behaviour: docs/content/docs/architecture.mdx:49-53,157, threat-model.mdx:176-189).
+ * Graph = CSR by destination: rowptr[n_nodes+1], col[E] source ids, ew[E] temporal weights. */
+
+/* K1 alone: m[r - row_begin] = sum_e ew_e * x[col_e] / max(sum_e ew_e, 1e-12) for rows
+ * [row_begin,row_end).  F in {32, 64, 128}.  m is [(row_end-row_begin), F]. */
+int nerrf_sage_aggregate(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                         const float* ew, float* m, int64_t n_nodes, int64_t row_begin,
+                         int64_t row_end, int F, nerrf_stream_t stream);
+
+/* One fused layer: out[v] = act([x_v || m_v] @ W + b) for v in [row_begin,row_end); out is the
+ * FULL [n_nodes, H] array (rows outside the range untouched).  W [2F, H], b [H]; H == 128. */
+int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                         const float* ew, const float* W, const float* b, float* out,
+                         int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
+                         int relu, int algo, nerrf_stream_t stream);
+
+/* Heads.  score[v] = sigmoid(h_v . node_w + node_b).  If edge_W != NULL also writes
+ * proj[v] = (h_v.We[0:H,0], h_v.We[0:H,1], h_v.We[H:2H,0], h_v.We[H:2H,1])  (proj [n,4]). */
+int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,
+                         const float* edge_W, float* proj, int64_t row_begin, int64_t row_end,
+                         int H, nerrf_stream_t stream);
+/* edge_logit[e] = proj[col_e][0:2] + proj[dst_e][2:4] + edge_b   (== [h_src||h_dst] @ We + be) */
+int nerrf_sage_edge_head(const float* proj, const void* rowptr, int rowptr_is64, const int32_t* col,
+                         const float* edge_b, float* edge_logit, int64_t row_begin,
+                         int64_t row_end, nerrf_stream_t stream);
+
+/* Whole forward on device pointers: L layers + node head.  W[l] is [2F_l, H], b[l] is [H]
+ * (host arrays of device pointers).  h_out [n_nodes,H]; score_out [n_nodes]; workspace must
+ * hold n_nodes*H floats when L > 1. */
+int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                       const float* ew, int64_t n_nodes, int f_in, int hidden, int num_layers,
+                       const float* const* W, const float* const* b, const float* node_w,
+                       float node_b, float* h_out, float* score_out, float* workspace,
+                       size_t workspace_bytes, int algo, nerrf_stream_t stream);
+
+/* Host-buffer session (the e2e call): device buffers live in the handle. */
+typedef struct nerrf_sage_session nerrf_sage_session;
+int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, int f_in, int hidden,
+                              int num_layers, nerrf_sage_session** out);
+/* weights are HOST pointers: W[l] [2F_l,H], b[l] [H], node_w [H]; copied to the device once. */
+int nerrf_sage_session_set_weights(nerrf_sage_session* s, const float* const* W,
+                                   const float* const* b, const float* node_w, float node_b);
+/* HOST in / HOST out: copies the graph + features H2D, runs forward, copies score (and h if
+ * h_out_host != NULL) D2H, synchronises. */
+int nerrf_sage_session_forward_host(nerrf_sage_session* s, const float* x_host,
+                                    const int32_t* rowptr_host, const int32_t* col_host,
+                                    const float* ew_host, int64_t n_nodes, int64_t n_edges,
+                                    float* score_out_host, float* h_out_host, int algo);
+int nerrf_sage_session_destroy(nerrf_sage_session* s);
+
+/* ------------------------------------------------------------------ rewards.score (row a6)
+ * Replaces: ai/planner/rewards.py (README.md:74,115 `Reward = -(data_loss + 0.1*downtime)`;
+ * threat-model.mdx:205-223).  states uint32 [B, n_words], n_words = 32*NW, NW = 1/2/4 for
+ * A <= 1024/2048/4096; action a = bit (a&31) of word (a>>5).  Bit-exact fixed-order fp32. */
+int nerrf_reward_score(const uint32_t* states, int64_t B, const float* p, const float* size,
+                       const float* cost, int A, float* out, nerrf_stream_t stream);
+
+/* ------------------------------------------------------------------ planner.mcts.search (a5)
+ * Replaces: ai/planner/mcts.py (README.md:74, ROADMAP.md:84; architecture.mdx:62-72).
+ * Leaf-parallel UCT, one persistent cooperative kernel for all T iterations.
+ * Workspace layout is private; query its size first.  Outputs: root_n int32 [A_pad],
+ * root_w fp32 [A_pad] (A_pad = 1024*NW), num_nodes int32 [1] -- all device pointers.
+ * ln_table: device fp32 [T+2], ln_table[k] = fp32(ln(k*R)).  R must be a power of two. */
+int nerrf_mcts_workspace_bytes(int A, int T, int R, size_t* bytes);
+int nerrf_mcts_search(const float* p, const float* size, const float* cost, int A,
+                      const uint32_t* root_state, int R, int D, int T, uint64_t seed, float c,
+                      float lo, float inv_range, const float* ln_table, int32_t* root_n,
+                      float* root_w, int32_t* num_nodes, void* workspace, size_t workspace_bytes,
+                      nerrf_stream_t stream);
+/* HOST in / HOST out convenience (allocates + frees device memory internally, synchronous).
+ * root_state_host may be NULL.  Also returns the tree arrays' root rows only. */
+int nerrf_mcts_search_host(const float* p, const float* size, const float* cost, int A,
+                           const uint32_t* root_state_host, int R, int D, int T, uint64_t seed,
+                           float c, float lo, float inv_range, const float* ln_table_host,
+                           int32_t* root_n_host, float* root_w_host, int32_t* num_nodes_host);
+
+/* ------------------------------------------------------------------ lstm.forward (row a4)
+ * Replaces: ai/models/lstm.py (README.md:73; architecture.mdx:55-59; threat-model.mdx:191-203).
+ * BiLSTM, torch.nn.LSTM gate order (i,f,g,o).  seq [B,T,D_in]; len int32 [B] (valid steps
+ * t < len[b]).  Weights per layer l and direction d (index 2*l+d), PRE-TRANSPOSED by the host:
+ *   Wih_t[2l+d] [D_l, 4H],  Whh_t[2l+d] [H, 4H],  bias[2l+d] [4H] (= b_ih + b_hh);
+ * D_0 = D_in, D_l = 2H.  head_W [2, 2H], head_b [2].  out [B,2] = sigmoid(head).
+ * workspace: 2 * B*T*2H floats (layer outputs ping-pong).  H must be 256; B any. */
+int nerrf_lstm_workspace_bytes(int64_t B, int T, int H, size_t* bytes);
+int nerrf_lstm_forward(const float* seq, const int32_t* len, int64_t B, int T, int D_in, int H,
+                       int num_layers, const float* const* Wih_t, const float* const* Whh_t,
+                       const float* const* bias, const float* head_W, const float* head_b,
+                       float* out, void* workspace, size_t workspace_bytes,
+                       nerrf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERRF_B200_H */
