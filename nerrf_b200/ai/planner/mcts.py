@@ -119,10 +119,22 @@ class Plan:
     searches: list          # SearchResult per step
 
 
+def ranked_children(root_n, root_w):
+    """Root children with n > 0 ordered by (n desc, Q desc, index asc) -- best_child() is element 0."""
+    n = np.asarray(root_n); w = np.asarray(root_w, np.float32)
+    idx = np.nonzero(n > 0)[0]
+    q = (w[idx] / n[idx].astype(np.float32)).astype(np.float32)
+    order = np.lexsort((idx, -q.astype(np.float64), -n[idx].astype(np.int64)))
+    return idx[order]
+
+
 def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096, depth: int = 50, seed: int = 0,
          c: float = math.sqrt(2.0), iterations: int = 64, device=None) -> Plan:
-    """Undo plan = repeated search / commit-best / re-root.  A step is kept only while the exact
-    reward of the committed state improves (the planner validates each step with rewards.score)."""
+    """Undo plan = repeated search / commit / re-root.  Each step the search ranks the root
+    children; the candidates are then VALIDATED with the exact reward (one batched
+    rewards.score call over all candidate next-states, mirroring the reference's "sandbox
+    validates, then apply" gate, architecture.mdx:81-86): the highest-ranked candidate whose
+    exact reward improves on the current state is committed; the plan ends when none does."""
     A = actions.A
     state = RW.empty_state(A)
     max_steps = depth if max_steps is None else max_steps
@@ -131,14 +143,16 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
     for step in range(max_steps):
         res = search(actions, None, n_rollouts, max(depth - step, 1), seed + step, c, iterations, state, device)
         out.searches.append(res)
-        a = res.best
-        if a < 0:
+        cand = ranked_children(res.root_n, res.root_w)
+        if cand.size == 0:
             break
-        nxt = state.copy()
-        nxt[a >> 5] |= np.uint32(1) << np.uint32(a & 31)
-        sc = float(RW.score(nxt[None, :], actions, device=device).cpu()[0])
-        if not sc > cur:
+        nxt = np.repeat(state[None, :], cand.size, axis=0)
+        nxt[np.arange(cand.size), cand >> 5] |= (np.uint32(1) << (cand & 31).astype(np.uint32)).astype(np.uint32)
+        sc = RW.score(nxt, actions, device=device).cpu().numpy()
+        better = np.nonzero(sc > np.float32(cur))[0]
+        if better.size == 0:
             break
-        state, cur = nxt, sc
-        out.actions.append(a); out.scores.append(sc)
+        k = int(better[0])
+        state, cur = nxt[k].copy(), float(sc[k])
+        out.actions.append(int(cand[k])); out.scores.append(cur)
     return out

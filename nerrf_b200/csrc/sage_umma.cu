@@ -1,10 +1,360 @@
-// tcgen05 fused GraphSAGE-T layer (placeholder until the UMMA kernel lands).
+// Fused GraphSAGE-T layer on 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   out[v, :] = act( [x_v || m_v] @ W + b ),   m_v = weighted mean of gathered source rows
+//
+// computed TRANSPOSED so that the small, reused operand lives in tensor memory:
+//
+//   D^T[H=128 features, rows] = W^T[128, K=2F] . X^T[K, rows]
+//     A operand = W^T, resident in TMEM for the whole (persistent) kernel, bf16 hi and lo halves
+//                 (lane = feature, two K elements per 32-bit column)
+//     B operand = the gathered tile X[rows, K] exactly as the gather warps produce it: row-major,
+//                 K contiguous == the UMMA "K-major" canonical layout (128-byte swizzle), bf16 hi/lo
+//     D         = fp32 accumulator in TMEM, [128 lanes x 64 columns] per tile, double buffered
+//
+// fp32-level accuracy from bf16 tensor cores (the north star's 1e-4 bound rules out plain
+// TF32/bf16): every fp32 value v is split v = hi + lo (hi = bf16(v), lo = bf16(v - hi)) and
+// three MMAs accumulate x_hi.w_hi + x_lo.w_hi + x_hi.w_lo in fp32 (error ~1e-5 relative).
+//
+// The aggregate never round-trips HBM: gather warps write hi/lo bf16 straight into the shared
+// memory B operand.  Warp roles in one CTA per SM (640 threads):
+//   warps 0-3   epilogue: tcgen05.ld accumulator (lane = feature), + bias, ReLU, 128 B/warp stores
+//   warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma, commit -> mbarriers)
+//   warps 5-19  gather: one CSR row per warp at a time (sage_gather.cuh), rows round-robin
+// Pipelines: smem stages full/empty (gather <-> MMA), TMEM accumulators full/empty (MMA <-> epilogue).
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "sage_gather.cuh"
+
 namespace nerrf {
-bool sage_umma_available() { return false; }
-int sage_layer_umma(const float*, const void*, int, const int32_t*, const float*, const float*, const float*, float*,
-                    int64_t, int64_t, int64_t, int, int, cudaStream_t) {
-    set_error("UMMA layer kernel not built");
+
+namespace {
+
+constexpr int TN = 64;                 // destination rows per tile (UMMA N)
+constexpr int UM = 128;                // UMMA M = hidden width
+constexpr int EPI_WARPS = 4;
+constexpr int MMA_WARP = 4;
+constexpr int GATHER_WARP0 = 5;
+constexpr int GATHER_WARPS = 15;
+constexpr int UMMA_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 640
+
+template <int F>
+struct UmmaCfg {
+    static constexpr int K = 2 * F;
+    static constexpr int KB = K / 64;                        // 128-byte K blocks
+    static constexpr int KSTEPS = K / 16;                    // MMAs (K=16) per product
+    static constexpr int PART_BYTES = KB * TN * 128;         // hi (or lo) half of one stage
+    static constexpr int STAGE_BYTES = 2 * PART_BYTES;
+    static constexpr int STAGES = (F == 128) ? 3 : (F == 64 ? 4 : 6);
+    static constexpr int ACC_COL0 = K;                       // W^T hi: [0,K/2)  lo: [K/2,K)
+    static constexpr int TMEM_COLS = (K + 2 * TN <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]^T   (kind::f16: bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1.
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                               // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // SBO = 1024 B
+    d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, N = TN, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+}
+
+// split 4 fp32 into bf16 hi / lo, packed (element 0 in the low half of word 0)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 f = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// byte offset of element (row r, k) inside one hi/lo part of a stage (k multiple of 4)
+__device__ __forceinline__ uint32_t b_offset(int r, int k) {
+    const int kb = k >> 6, col = k & 63;
+    const int chunk = col >> 3;                            // 16-byte chunk in the 128-byte row
+    return (uint32_t)(kb * (TN * 128) + r * 128 + (((chunk ^ (r & 7)) << 4) | ((col & 7) << 1)));
+}
+
+template <int F, typename RP>
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
+                       float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu) {
+    using C = UmmaCfg<F>;
+    constexpr int K = C::K, LPR = F / 4;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
+    unsigned char* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto accf_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto acce_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t rows = row_end - row_begin;
+    const int64_t n_tiles = (rows + TN - 1) / TN;
+
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), TN); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), EPI_WARPS * 32); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    // ---- W^T -> TMEM (hi | lo), done once per CTA by the four epilogue warps: thread = feature
+    float my_bias = 0.f;
+    if (warp < EPI_WARPS) {
+        const int f = warp * 32 + lane;
+        my_bias = __ldg(bias + f);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a = __ldg(W + (size_t)(k0 + 2 * i) * UM + f);
+                const float b = __ldg(W + (size_t)(k0 + 2 * i + 1) * UM + f);
+                split2(a, b, hi[i], lo[i]);
+            }
+            tmem_st8(lane_addr + (uint32_t)(k0 >> 1), hi);
+            tmem_st8(lane_addr + (uint32_t)(K / 2 + (k0 >> 1)), lo);
+        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp >= GATHER_WARP0) {
+        // =========================================================== gather warps (producers)
+        const int g = warp - GATHER_WARP0;
+        int64_t last_tl = -1;
+        for (int64_t i = g;; i += GATHER_WARPS) {
+            const int64_t tl = i / TN;                                  // tile index in this CTA's sequence
+            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
+            if (tile >= n_tiles) break;
+            const int r = (int)(i % TN);
+            const int s = (int)(tl % C::STAGES);
+            const uint32_t n = (uint32_t)(tl / C::STAGES);
+            if (tl != last_tl) {                                         // first row of this tile for this warp
+                mbar_wait(empty_bar(s), (n & 1u) ^ 1u);
+                last_tl = tl;
+            }
+            const int64_t row = row_begin + tile * TN + r;
+            if (row < row_end) {
+                const int64_t e0 = rowptr[row], e1 = rowptr[row + 1];
+                float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < LPR) self = ldg4(x + row * F + 4 * lane);
+                const float4 mean = gather_row<F>(x, col, ew, e0, e1, lane);
+                if (lane < LPR) {
+                    unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
+                    uint2 hi, lo;
+                    split4(self, hi, lo);
+                    uint32_t off = b_offset(r, 4 * lane);
+                    *reinterpret_cast<uint2*>(st + off) = hi;
+                    *reinterpret_cast<uint2*>(st + C::PART_BYTES + off) = lo;
+                    split4(mean, hi, lo);
+                    off = b_offset(r, F + 4 * lane);
+                    *reinterpret_cast<uint2*>(st + off) = hi;
+                    *reinterpret_cast<uint2*>(st + C::PART_BYTES + off) = lo;
+                }
+                fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc();
+            for (int64_t tl = 0;; ++tl) {
+                const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
+                if (tile >= n_tiles) break;
+                const int s = (int)(tl % C::STAGES);
+                const uint32_t n = (uint32_t)(tl / C::STAGES);
+                const int a = (int)(tl & 1);
+                const uint32_t m = (uint32_t)(tl >> 1);
+                mbar_wait(acce_bar(a), (m & 1u) ^ 1u);                   // epilogue drained this accumulator
+                mbar_wait(full_bar(s), n & 1u);                          // gather filled this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(C::ACC_COL0 + a * TN);
+                const uint32_t st_hi = smem_base + (uint32_t)(s * C::STAGE_BYTES);
+                const uint32_t st_lo = st_hi + (uint32_t)C::PART_BYTES;
+#pragma unroll 4
+                for (int j = 0; j < C::KSTEPS; ++j) {
+                    const uint32_t boff = (uint32_t)((j >> 2) * (TN * 128) + (j & 3) * 32);
+                    const uint64_t b_hi = make_b_desc(st_hi + boff), b_lo = make_b_desc(st_lo + boff);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(j * 8), a_lo = tmem_base + (uint32_t)(K / 2 + j * 8);
+                    umma_ts(d_tmem, a_hi, b_hi, idesc, j > 0 ? 1u : 0u);
+                    umma_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+                    umma_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));                               // smem stage reusable once the MMAs retire
+                umma_commit(accf_bar(a));                                // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // =========================================================== epilogue warps
+        const int f = warp * 32 + lane;
+        for (int64_t tl = 0;; ++tl) {
+            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
+            if (tile >= n_tiles) break;
+            const int a = (int)(tl & 1);
+            const uint32_t m = (uint32_t)(tl >> 1);
+            mbar_wait(accf_bar(a), m & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::ACC_COL0 + a * TN);
+            const int64_t row0 = row_begin + tile * TN;
+#pragma unroll
+            for (int half = 0; half < TN / 32; ++half) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(half * 32), v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t row = row0 + half * 32 + j;
+                    float o = __uint_as_float(v[j]) + my_bias;
+                    if (relu) o = fmaxf(o, 0.f);
+                    if (row < row_end) out[row * UM + f] = o;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acce_bar(a));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int F, typename RP>
+int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
+                float* out, int64_t row_begin, int64_t row_end, int relu, cudaStream_t st) {
+    using C = UmmaCfg<F>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set = true;
+    }
+    const int64_t rows = row_end - row_begin;
+    const int64_t tiles = (rows + TN - 1) / TN;
+    if (tiles == 0) return NERRF_OK;
+    const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+    sage_layer_umma_kernel<F, RP><<<(unsigned)grid, UMMA_THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu);
+    return launch_status("sage_layer_umma_kernel");
+}
+
+}  // namespace
+
+bool sage_umma_available() { return true; }
+
+int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
+                    const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
+                    cudaStream_t st) {
+    (void)n_nodes;
+#define GO(FV)                                                                                                        \
+    return is64 ? launch_umma<FV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st) \
+                : launch_umma<FV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st)
+    switch (F) {
+        case 32: GO(32);
+        case 64: GO(64);
+        case 128: GO(128);
+    }
+#undef GO
+    set_error("UMMA layer: unsupported feature width F=%d (supported: 32, 64, 128)", F);
     return NERRF_ERR_INVALID;
 }
+
 }  // namespace nerrf
