@@ -311,7 +311,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "umma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "umma", "umma2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

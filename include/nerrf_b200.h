@@ -38,7 +38,9 @@ extern "C" {
 /* algo selector for the GraphSAGE-T layer */
 #define NERRF_SAGE_ALGO_AUTO 0
 #define NERRF_SAGE_ALGO_FFMA 1   /* fused gather+aggregate -> fp32 CUDA-core GEMM           */
-#define NERRF_SAGE_ALGO_UMMA 2   /* fused gather+aggregate -> tcgen05 bf16x3 GEMM (TMEM)    */
+#define NERRF_SAGE_ALGO_UMMA 2   /* fused gather+aggregate -> tcgen05 GEMM, 3-term bf16 split
+                                    (6 MMAs per K step; fp32-equivalent accuracy)           */
+#define NERRF_SAGE_ALGO_UMMA2 3  /* same with a 2-term split (3 MMAs; ~1e-5 relative)       */
 
 typedef void* nerrf_stream_t;    /* cudaStream_t */
 

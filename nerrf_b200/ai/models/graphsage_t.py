@@ -20,7 +20,7 @@ from torch import nn
 
 from ... import _lib as L
 
-ALGOS = {"auto": 0, "ffma": 1, "umma": 2}
+ALGOS = {"auto": 0, "ffma": 1, "umma": 2, "umma2": 3}
 
 
 class GraphSAGE_T(nn.Module):

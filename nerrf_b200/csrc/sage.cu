@@ -12,7 +12,7 @@ namespace nerrf {
 
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew,
                     const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin,
-                    int64_t row_end, int F, int relu, cudaStream_t st);   // sage_umma.cu
+                    int64_t row_end, int F, int relu, int nsplit, cudaStream_t st);   // sage_umma.cu
 bool sage_umma_available();
 
 // ------------------------------------------------------------------------------------------
@@ -239,7 +239,8 @@ static int layer_dispatch(const float* x, const RP* rowptr, const int32_t* col, 
 
 static int check_graph_args(const void* x, const void* rowptr, const void* col, const void* ew, int64_t n_nodes,
                             int64_t row_begin, int64_t row_end) {
-    NERRF_REQUIRE(x && rowptr && col && ew, "null graph pointer");
+    NERRF_REQUIRE(x && rowptr, "null graph pointer");   // col / ew may be null when the graph has no edges
+    (void)col; (void)ew;
     NERRF_REQUIRE(n_nodes >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= n_nodes,
                   "bad row range [%lld,%lld) for %lld nodes", (long long)row_begin, (long long)row_end, (long long)n_nodes);
     NERRF_REQUIRE(((uintptr_t)x & 15) == 0, "x must be 16-byte aligned");
@@ -288,8 +289,9 @@ extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowp
     NERRF_REQUIRE(x != out, "in-place layer is not supported");
     cudaStream_t st = (cudaStream_t)stream;
     if (algo == NERRF_SAGE_ALGO_AUTO) algo = sage_umma_available() && (F == 32 || F == 128) ? NERRF_SAGE_ALGO_UMMA : NERRF_SAGE_ALGO_FFMA;
-    if (algo == NERRF_SAGE_ALGO_UMMA)
-        return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu, st);
+    if (algo == NERRF_SAGE_ALGO_UMMA || algo == NERRF_SAGE_ALGO_UMMA2)
+        return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu,
+                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, st);
     NERRF_REQUIRE(algo == NERRF_SAGE_ALGO_FFMA, "unknown algo %d", algo);
     if (rowptr_is64)
         return layer_dispatch<int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st);

@@ -37,17 +37,23 @@ constexpr int GATHER_WARP0 = 5;
 constexpr int GATHER_WARPS = 15;
 constexpr int UMMA_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 640
 
-template <int F>
+// NS = number of bf16 terms each fp32 value is split into (v = p0 + p1 [+ p2], p_i = bf16 of the
+// running residual).  NS = 3 with the six products (x0w0, x1w0, x0w1, x1w1, x2w0, x0w2) drops only
+// terms below 2^-24: fp32-equivalent.  NS = 2 with three products is ~1e-5 relative.
+template <int F, int NS>
 struct UmmaCfg {
     static constexpr int K = 2 * F;
     static constexpr int KB = K / 64;                        // 128-byte K blocks
     static constexpr int KSTEPS = K / 16;                    // MMAs (K=16) per product
-    static constexpr int PART_BYTES = KB * TN * 128;         // hi (or lo) half of one stage
-    static constexpr int STAGE_BYTES = 2 * PART_BYTES;
-    static constexpr int STAGES = (F == 128) ? 3 : (F == 64 ? 4 : 6);
-    static constexpr int ACC_COL0 = K;                       // W^T hi: [0,K/2)  lo: [K/2,K)
-    static constexpr int TMEM_COLS = (K + 2 * TN <= 256) ? 256 : 512;
+    static constexpr int PART_BYTES = KB * TN * 128;         // one bf16 term of one stage
+    static constexpr int STAGE_BYTES = NS * PART_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int W_PART_COLS = K / 2;                // W^T term p lives in TMEM columns [p*K/2, (p+1)*K/2)
+    static constexpr int ACC_COL0 = NS * W_PART_COLS;
+    static constexpr int TMEM_COLS = (ACC_COL0 + 2 * TN <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "need at least two smem stages");
+    static_assert(ACC_COL0 + 2 * TN <= 512, "TMEM overflow");
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -130,21 +136,26 @@ __host__ __device__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 }
 
-// split 4 fp32 into bf16 hi / lo, packed (element 0 in the low half of word 0)
-__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+// split fp32 values into NS bf16 terms of the running residual; pairs packed (first element low)
+template <int NS>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t (&parts)[NS]) {
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        parts[p] = *reinterpret_cast<const uint32_t*>(&h);
+        if (p + 1 < NS) {
+            const float2 f = __bfloat1622float2(h);
+            a -= f.x; b -= f.y;                        // exact: the residual is representable in fp32
+        }
+    }
 }
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const float2 f = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - f.x, b - f.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+template <int NS>
+__device__ __forceinline__ void split4(const float4 v, uint2 (&parts)[NS]) {
+    uint32_t lo[NS], hi[NS];
+    split_pair<NS>(v.x, v.y, lo);
+    split_pair<NS>(v.z, v.w, hi);
+#pragma unroll
+    for (int p = 0; p < NS; ++p) parts[p] = make_uint2(lo[p], hi[p]);
 }
 
 // byte offset of element (row r, k) inside one hi/lo part of a stage (k multiple of 4)
@@ -154,12 +165,12 @@ __device__ __forceinline__ uint32_t b_offset(int r, int k) {
     return (uint32_t)(kb * (TN * 128) + r * 128 + (((chunk ^ (r & 7)) << 4) | ((col & 7) << 1)));
 }
 
-template <int F, typename RP>
+template <int F, int NS, typename RP>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
                        float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu) {
-    using C = UmmaCfg<F>;
+    using C = UmmaCfg<F, NS>;
     constexpr int K = C::K, LPR = F / 4;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
@@ -197,15 +208,18 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         my_bias = __ldg(bias + f);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int k0 = 0; k0 < K; k0 += 16) {
-            uint32_t hi[8], lo[8];
+            uint32_t parts[NS][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float a = __ldg(W + (size_t)(k0 + 2 * i) * UM + f);
                 const float b = __ldg(W + (size_t)(k0 + 2 * i + 1) * UM + f);
-                split2(a, b, hi[i], lo[i]);
+                uint32_t pp[NS];
+                split_pair<NS>(a, b, pp);
+#pragma unroll
+                for (int p = 0; p < NS; ++p) parts[p][i] = pp[p];
             }
-            tmem_st8(lane_addr + (uint32_t)(k0 >> 1), hi);
-            tmem_st8(lane_addr + (uint32_t)(K / 2 + (k0 >> 1)), lo);
+#pragma unroll
+            for (int p = 0; p < NS; ++p) tmem_st8(lane_addr + (uint32_t)(p * C::W_PART_COLS + (k0 >> 1)), parts[p]);
         }
         tmem_wait_st();
     }
@@ -236,15 +250,15 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 const float4 mean = gather_row<F>(x, col, ew, e0, e1, lane);
                 if (lane < LPR) {
                     unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
-                    uint2 hi, lo;
-                    split4(self, hi, lo);
+                    uint2 parts[NS];
+                    split4<NS>(self, parts);
                     uint32_t off = b_offset(r, 4 * lane);
-                    *reinterpret_cast<uint2*>(st + off) = hi;
-                    *reinterpret_cast<uint2*>(st + C::PART_BYTES + off) = lo;
-                    split4(mean, hi, lo);
+#pragma unroll
+                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+                    split4<NS>(mean, parts);
                     off = b_offset(r, F + 4 * lane);
-                    *reinterpret_cast<uint2*>(st + off) = hi;
-                    *reinterpret_cast<uint2*>(st + C::PART_BYTES + off) = lo;
+#pragma unroll
+                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
                 }
                 fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
             }
@@ -266,16 +280,25 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 mbar_wait(full_bar(s), n & 1u);                          // gather filled this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(C::ACC_COL0 + a * TN);
-                const uint32_t st_hi = smem_base + (uint32_t)(s * C::STAGE_BYTES);
-                const uint32_t st_lo = st_hi + (uint32_t)C::PART_BYTES;
-#pragma unroll 4
+                const uint32_t st0 = smem_base + (uint32_t)(s * C::STAGE_BYTES);
+#pragma unroll 2
                 for (int j = 0; j < C::KSTEPS; ++j) {
                     const uint32_t boff = (uint32_t)((j >> 2) * (TN * 128) + (j & 3) * 32);
-                    const uint64_t b_hi = make_b_desc(st_hi + boff), b_lo = make_b_desc(st_lo + boff);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(j * 8), a_lo = tmem_base + (uint32_t)(K / 2 + j * 8);
-                    umma_ts(d_tmem, a_hi, b_hi, idesc, j > 0 ? 1u : 0u);
-                    umma_ts(d_tmem, a_hi, b_lo, idesc, 1u);
-                    umma_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+                    uint64_t xb[NS];
+                    uint32_t wa[NS];
+#pragma unroll
+                    for (int p = 0; p < NS; ++p) {
+                        xb[p] = make_b_desc(st0 + (uint32_t)(p * C::PART_BYTES) + boff);     // x term p (smem)
+                        wa[p] = tmem_base + (uint32_t)(p * C::W_PART_COLS + j * 8);          // W^T term p (TMEM)
+                    }
+                    umma_ts(d_tmem, wa[0], xb[0], idesc, j > 0 ? 1u : 0u);
+                    umma_ts(d_tmem, wa[0], xb[1], idesc, 1u);
+                    umma_ts(d_tmem, wa[1], xb[0], idesc, 1u);
+                    if constexpr (NS == 3) {
+                        umma_ts(d_tmem, wa[1], xb[1], idesc, 1u);
+                        umma_ts(d_tmem, wa[0], xb[2], idesc, 1u);
+                        umma_ts(d_tmem, wa[2], xb[0], idesc, 1u);
+                    }
                 }
                 umma_commit(empty_bar(s));                               // smem stage reusable once the MMAs retire
                 umma_commit(accf_bar(a));                                // accumulator ready for the epilogue
@@ -319,20 +342,20 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     }
 }
 
-template <int F, typename RP>
+template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, cudaStream_t st) {
-    using C = UmmaCfg<F>;
+    using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
-        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_set = true;
     }
     const int64_t rows = row_end - row_begin;
     const int64_t tiles = (rows + TN - 1) / TN;
     if (tiles == 0) return NERRF_OK;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    sage_layer_umma_kernel<F, RP><<<(unsigned)grid, UMMA_THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu);
+    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, UMMA_THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu);
     return launch_status("sage_layer_umma_kernel");
 }
 
@@ -342,18 +365,26 @@ bool sage_umma_available() { return true; }
 
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
-                    cudaStream_t st) {
+                    int nsplit, cudaStream_t st) {
     (void)n_nodes;
-#define GO(FV)                                                                                                        \
-    return is64 ? launch_umma<FV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st) \
-                : launch_umma<FV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st)
-    switch (F) {
-        case 32: GO(32);
-        case 64: GO(64);
-        case 128: GO(128);
+#define GO(FV, NSV)                                                                                                          \
+    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st) \
+                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st)
+    if (nsplit == 3) {
+        switch (F) {
+            case 32: GO(32, 3);
+            case 64: GO(64, 3);
+            case 128: GO(128, 3);
+        }
+    } else if (nsplit == 2) {
+        switch (F) {
+            case 32: GO(32, 2);
+            case 64: GO(64, 2);
+            case 128: GO(128, 2);
+        }
     }
 #undef GO
-    set_error("UMMA layer: unsupported feature width F=%d (supported: 32, 64, 128)", F);
+    set_error("UMMA layer: unsupported feature width F=%d / split %d (supported: F in 32, 64, 128; split 2 or 3)", F, nsplit);
     return NERRF_ERR_INVALID;
 }
 

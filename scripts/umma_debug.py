@@ -7,9 +7,11 @@ from nerrf_b200 import graph as G
 from oracle import sage_ref as S
 
 torch.manual_seed(0)
-for F in (32, 128, 64):
+import itertools
+for F, algo in itertools.product((32, 128, 64), ("umma", "umma2")):
+    print("----", F, algo)
     N = 64 * 3 + 5
-    model = GraphSAGE_T(F, 128, 1, algo="umma").cuda()
+    model = GraphSAGE_T(F, 128, 1, algo=algo).cuda()
     W = model.weights[0].detach().cpu(); b = model.biases[0].detach().cpu()
     rp = torch.zeros(N + 1, dtype=torch.int32, device="cuda")
     col = torch.zeros(0, dtype=torch.int32, device="cuda"); ew = torch.zeros(0, device="cuda")

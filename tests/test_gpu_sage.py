@@ -11,20 +11,10 @@ from oracle import sage_ref as S
 from gpu_util import dev_graph, cpu_graph, assert_close_fp32
 
 pytestmark = pytest.mark.gpu
-ALGOS = ["ffma", "umma"]
-
-
-def _skip_if_no_umma(algo):
-    if algo == "umma":
-        x = torch.zeros(128, 32, device="cuda"); rp = torch.zeros(129, dtype=torch.int32, device="cuda")
-        c = torch.zeros(1, dtype=torch.int32, device="cuda"); w = torch.zeros(1, device="cuda")
-        m = GraphSAGE_T(32, 128, 1, algo="umma").cuda()
-        try:
-            m.layer_forward(0, x, rp, c[:0], w[:0])
-        except L.NerrfError as e:
-            if "not built" in str(e):
-                pytest.skip("UMMA kernel not built")
-            raise
+ALGOS = ["ffma", "umma", "umma2"]
+# "umma2" (2-term bf16 split) is ~1e-5 relative to the tensor scale: within the north star's 1e-4 bound
+# but not within the strict absolute floor used for the fp32-equivalent paths.
+ATOL_RMS = {"ffma": 1e-5, "umma": 1e-5, "umma2": 1e-4, "auto": 1e-5}
 
 
 @pytest.mark.parametrize("F", [32, 64, 128])
@@ -42,17 +32,16 @@ def test_aggregate_parity(F):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("F", [32, 128])
+@pytest.mark.parametrize("F", [32, 64, 128])
 @pytest.mark.parametrize("hub", ["src", "dst"])
 def test_layer_parity(algo, F, hub):
-    _skip_if_no_umma(algo)
     g = G.synthetic_graph(N=5000, E=60000, seed=5, hub=hub, f_in=F)
     model = GraphSAGE_T(F, 128, 1, algo=algo).cuda()
     x, rp, col, ew = dev_graph(g)
     out = model.layer_forward(0, x, rp, col, ew)
     W, b = model.oracle_params()["layers"][0]
     want = S.layer(*cpu_graph(g), W, b)
-    assert_close_fp32(out, want, what=f"layer {algo} F={F} hub={hub}")
+    assert_close_fp32(out, want, atol_rms=ATOL_RMS[algo], what=f"layer {algo} F={F} hub={hub}")
     # int64 rowptr gives bit-identical output
     out64 = model.layer_forward(0, x, rp.long(), col, ew)
     assert torch.equal(out, out64)
@@ -60,7 +49,6 @@ def test_layer_parity(algo, F, hub):
 
 @pytest.mark.parametrize("algo", ALGOS)
 def test_layer_edge_cases(algo):
-    _skip_if_no_umma(algo)
     model = GraphSAGE_T(32, 128, 1, algo=algo).cuda()
     W, b = model.oracle_params()["layers"][0]
     # (a) no edges at all, N not a multiple of the tile; (b) one node; (c) a single hub row with every edge
@@ -71,7 +59,7 @@ def test_layer_edge_cases(algo):
         rowptr, col, ew = G.csr_from_edges(src, dst, t, conf, N)
         g = G.TemporalGraph(rowptr, col, ew, rng.standard_normal((N, 32)).astype(np.float32), {})
         out = model.layer_forward(0, *dev_graph(g))
-        assert_close_fp32(out, S.layer(*cpu_graph(g), W, b), what=f"edge case N={N} E={E}")
+        assert_close_fp32(out, S.layer(*cpu_graph(g), W, b), atol_rms=ATOL_RMS[algo], what=f"edge case N={N} E={E}")
     # (d) row range: only [row_begin,row_end) is written
     g = G.synthetic_graph(N=1000, E=9000, seed=2)
     x, rp, col, ew = dev_graph(g)
@@ -84,13 +72,12 @@ def test_layer_edge_cases(algo):
 @pytest.mark.parametrize("algo", ALGOS)
 def test_forward_parity_and_indices(algo):
     """3-layer forward + heads; anomalous-node indices (top-k by score) must be bit-exact."""
-    _skip_if_no_umma(algo)
     g = G.synthetic_graph(N=20000, E=200000, seed=20250115)
     model = GraphSAGE_T(32, 128, 3, algo=algo).cuda()
     h, sc, el = model(*dev_graph(g), return_edge_logits=True)
     hw, scw, elw = S.forward(model.oracle_params(), *cpu_graph(g), edge_logits=True)
-    assert_close_fp32(h, hw, what="h")
-    assert_close_fp32(sc, scw, what="node_score")
+    assert_close_fp32(h, hw, atol_rms=ATOL_RMS[algo], what="h")
+    assert_close_fp32(sc, scw, atol_rms=ATOL_RMS[algo], what="node_score")
     assert_close_fp32(el, elw, rtol=1e-4, atol_rms=1e-4, what="edge_logit")
     k = 64
     top_gpu = torch.topk(sc.cpu(), k).indices
