@@ -16,11 +16,15 @@
 // three MMAs accumulate x_hi.w_hi + x_lo.w_hi + x_hi.w_lo in fp32 (error ~1e-5 relative).
 //
 // The aggregate never round-trips HBM: gather warps write hi/lo bf16 straight into the shared
-// memory B operand.  Warp roles in one CTA per SM (640 threads):
+// memory B operand.  Warp roles in one CTA per SM (512 threads):
 //   warps 0-3   epilogue: tcgen05.ld accumulator (lane = feature), + bias, ReLU, 128 B/warp stores
 //   warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma, commit -> mbarriers)
-//   warps 5-19  gather: one CSR row per warp at a time (sage_gather.cuh), rows round-robin
-// Pipelines: smem stages full/empty (gather <-> MMA), TMEM accumulators full/empty (MMA <-> epilogue).
+//   warp  5     edge-block loader: stages each tile's rowptr / col / ew slice into shared memory with
+//               cp.async (completion on an mbarrier), running up to IDX_STAGES tiles ahead
+//   warps 6-15  gather: one CSR row per warp at a time (sage_gather.cuh), rows round-robin; indices
+//               come from shared memory, so the only global latency a row exposes is its x rows
+// Pipelines: idx stages full/empty (loader <-> gather), smem operand stages full/empty (gather <-> MMA),
+// TMEM accumulators full/empty (MMA <-> epilogue).
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "sage_gather.cuh"
@@ -29,13 +33,19 @@ namespace nerrf {
 
 namespace {
 
-constexpr int TN = 64;                 // destination rows per tile (UMMA N)
+constexpr int TN = 32;                 // destination rows per tile (UMMA N)
 constexpr int UM = 128;                // UMMA M = hidden width
 constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
-constexpr int GATHER_WARP0 = 5;
-constexpr int GATHER_WARPS = 15;
+constexpr int LOADER_WARP = 5;
+constexpr int GATHER_WARP0 = 6;
+constexpr int GATHER_WARPS = 14;
 constexpr int UMMA_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 640
+constexpr int IDX_STAGES = 3;
+constexpr int EMAX = 512;              // staged edges per tile (4 KB); the rest of a heavier tile is read from global
+constexpr int IDX_STAGE_BYTES = EMAX * 8 + 512;      // col[EMAX] | ew[EMAX] | rp[TN+1] (relative) | e_lo (int64)
+constexpr int QS = 4;                  // items (source rows) per sub-batch = one cp.async group
+constexpr int NQ = 4;                  // sub-batch slots in a warp's ring; NQ-1 groups are in flight
 
 // NS = number of bf16 terms each fp32 value is split into (v = p0 + p1 [+ p2], p_i = bf16 of the
 // running residual).  NS = 3 with the six products (x0w0, x1w0, x0w1, x1w1, x2w0, x0w2) drops only
@@ -47,11 +57,14 @@ struct UmmaCfg {
     static constexpr int KSTEPS = K / 16;                    // MMAs (K=16) per product
     static constexpr int PART_BYTES = KB * TN * 128;         // one bf16 term of one stage
     static constexpr int STAGE_BYTES = NS * PART_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int RING_BYTES = NQ * QS * F * 4;       // per gather warp: NQ sub-batches x QS source rows
+    static constexpr int STAGES = (F == 128) ? 2 : 4;
     static constexpr int W_PART_COLS = K / 2;                // W^T term p lives in TMEM columns [p*K/2, (p+1)*K/2)
     static constexpr int ACC_COL0 = NS * W_PART_COLS;
     static constexpr int TMEM_COLS = (ACC_COL0 + 2 * TN <= 256) ? 256 : 512;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + IDX_STAGES * IDX_STAGE_BYTES +
+                                   (size_t)GATHER_WARPS * RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least two smem stages");
     static_assert(ACC_COL0 + 2 * TN <= 512, "TMEM overflow");
 };
@@ -76,6 +89,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// same, with a suspend-time hint: for the roles that have slack (they should not burn issue slots spinning)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (does not add to the pending count)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -175,12 +214,17 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
     unsigned char* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t idx_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bar_base = idx_base + IDX_STAGES * IDX_STAGE_BYTES;     // 256 B of barriers, then the gather rings
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto accf_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto acce_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    auto idxf_bar = [&](int q) { return bar_base + 8u * (2 * C::STAGES + 4 + q); };
+    auto idxe_bar = [&](int q) { return bar_base + 8u * (2 * C::STAGES + 4 + IDX_STAGES + q); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4 + 2 * IDX_STAGES);
+    unsigned char* idx_gen = smem_gen + (idx_base - smem_base);
+    const uint32_t ring_base = bar_base + 256;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,6 +235,8 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         if (lane == 0) {
             for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), TN); mbar_init(empty_bar(s), 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), EPI_WARPS * 32); }
+            // idx full: 32 async (cp.async) arrivals + 1 release-arrive for the rowptr words; empty: one per gather warp
+            for (int q = 0; q < IDX_STAGES; ++q) { mbar_init(idxf_bar(q), 33); mbar_init(idxe_bar(q), GATHER_WARPS); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -228,42 +274,199 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     tc_fence_after();
 
     if (warp >= GATHER_WARP0) {
-        // =========================================================== gather warps (producers)
+        // =========================================================== gather warps (producers of the B operand)
+        // Row stream of this warp: i = g, g+G, g+2G, ... over the CTA's tiles.  A row is the item list
+        // [self, edge_0 .. edge_{deg-1}], cut into sub-batches of QS items.  Every sub-batch is one cp.async
+        // group that lands QS source rows in a slot of this warp's shared-memory ring; NQ-1 groups stay in
+        // flight while the oldest is consumed (LDS + FFMA), so memory-level parallelism is bounded by the
+        // ring, not by registers, and no load ever stalls a scoreboard.
+        constexpr int G = 32 / LPR;                                     // items fetched by one warp instruction
         const int g = warp - GATHER_WARP0;
-        int64_t last_tl = -1;
-        for (int64_t i = g;; i += GATHER_WARPS) {
-            const int64_t tl = i / TN;                                  // tile index in this CTA's sequence
+        const int grp = lane / LPR, sub = lane % LPR;
+        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES);
+        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_u32 - smem_base));
+        const float* xs = x + 4 * sub;
+
+        struct Cursor {
+            int64_t i;          // position in the row stream
+            int64_t tl;         // tile (in this CTA's sequence) of row i, -1 = none loaded
+            int b, nb;          // sub-batch within the row, number of sub-batches
+            int e0, deg;        // first edge (relative to the tile's e_lo) and in-degree
+            const int32_t* col_s; const float* ew_s; const int32_t* rp_s; int64_t e_lo;
+            bool valid;         // row exists (tile in range and row < row_end)
+            bool live;          // cursor still inside the CTA's tile sequence
+        };
+        auto load_row = [&](Cursor& c, bool wait_idx) {
+            const int64_t tl = c.i / TN;
             const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-            if (tile >= n_tiles) break;
-            const int r = (int)(i % TN);
-            const int s = (int)(tl % C::STAGES);
-            const uint32_t n = (uint32_t)(tl / C::STAGES);
-            if (tl != last_tl) {                                         // first row of this tile for this warp
-                mbar_wait(empty_bar(s), (n & 1u) ^ 1u);
-                last_tl = tl;
+            c.live = tile < n_tiles;
+            c.valid = false; c.b = 0; c.nb = 1; c.deg = 0; c.e0 = 0;
+            if (!c.live) return;
+            if (tl != c.tl) {
+                const int q = (int)(tl % IDX_STAGES);
+                if (wait_idx) mbar_wait(idxf_bar(q), (uint32_t)(tl / IDX_STAGES) & 1u);      // edge block staged
+                unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
+                c.col_s = reinterpret_cast<const int32_t*>(ib);
+                c.ew_s = reinterpret_cast<const float*>(ib + EMAX * 4);
+                c.rp_s = reinterpret_cast<const int32_t*>(ib + EMAX * 8);
+                c.e_lo = *reinterpret_cast<const int64_t*>(ib + EMAX * 8 + 384);
+                c.tl = tl;
             }
+            const int r = (int)(c.i % TN);
             const int64_t row = row_begin + tile * TN + r;
             if (row < row_end) {
-                const int64_t e0 = rowptr[row], e1 = rowptr[row + 1];
-                float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < LPR) self = ldg4(x + row * F + 4 * lane);
-                const float4 mean = gather_row<F>(x, col, ew, e0, e1, lane);
-                if (lane < LPR) {
-                    unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
-                    uint2 parts[NS];
-                    split4<NS>(self, parts);
-                    uint32_t off = b_offset(r, 4 * lane);
-#pragma unroll
-                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
-                    split4<NS>(mean, parts);
-                    off = b_offset(r, F + 4 * lane);
-#pragma unroll
-                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
-                }
-                fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
+                c.valid = true;
+                c.e0 = c.rp_s[r];
+                c.deg = c.rp_s[r + 1] - c.e0;
+                c.nb = (c.deg + 1 + QS - 1) / QS;
             }
+        };
+        auto advance = [&](Cursor& c, bool wait_idx) {
+            if (++c.b < c.nb) return;
+            c.i += GATHER_WARPS;
+            load_row(c, wait_idx);
+        };
+        // issue the cp.async group of the sub-batch under cursor `c` into ring slot `slot`
+        auto issue = [&](const Cursor& c, int slot) {
+            if (c.live && c.valid) {
+                const int64_t row = row_begin + ((int64_t)blockIdx.x + c.tl * gridDim.x) * TN + (c.i % TN);
+#pragma unroll
+                for (int t = 0; t < QS; t += G) {
+                    const int item = c.b * QS + t + grp;                 // 0 = self, k >= 1 = edge k-1
+                    if (item <= c.deg) {
+                        int64_t src = row;
+                        if (item > 0) {
+                            const int k = c.e0 + item - 1;
+                            src = (k < EMAX) ? c.col_s[k] : __ldg(col + c.e_lo + k);
+                        }
+                        cp_async16(ring_u32 + (uint32_t)(((slot * QS + t + grp) * F + 4 * sub) * 4), xs + src * F);
+                    }
+                }
+            }
+            cp_async_commit();                                            // (possibly empty) group keeps the count in step
+        };
+
+        Cursor ci, cc;                                                    // issue / consume cursors
+        ci.i = g; ci.tl = -1; load_row(ci, true);
+        cc = ci;
+        int islot = 0, cslot = 0;
+#pragma unroll
+        for (int d = 0; d < NQ - 1; ++d) {                               // prologue: NQ-1 groups in flight
+            issue(ci, islot);
+            islot = (islot + 1) % NQ;
+            if (ci.live) advance(ci, true);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), self = acc;
+        float wsum = 0.f;
+        int64_t last_tl = -1;
+        while (cc.live) {
+            cp_async_wait<NQ - 2>();                                      // oldest group landed (this lane's part) ...
+            __syncwarp();                                                 // ... and everyone else's
+            if (cc.valid) {
+#pragma unroll
+                for (int t = 0; t < QS; t += G) {
+                    const int item = cc.b * QS + t + grp;
+                    if (item <= cc.deg) {
+                        const float4 v = *reinterpret_cast<const float4*>(ring_gen + ((cslot * QS + t + grp) * F + 4 * sub));
+                        if (item == 0) {
+                            self = v;
+                        } else {
+                            const int k = cc.e0 + item - 1;
+                            const float w = (k < EMAX) ? cc.ew_s[k] : __ldg(ew + cc.e_lo + k);
+                            wsum += w;
+                            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                                 // slot fully read before it is refilled
+            issue(ci, islot);                                             // refill the ring
+            islot = (islot + 1) % NQ;
+            if (ci.live) advance(ci, true);
+            cslot = (cslot + 1) % NQ;
+
+            if (cc.b + 1 == cc.nb) {
+                // ---- row complete: normalise, split to bf16 terms, write the UMMA B operand, signal
+                const int64_t tl = cc.tl;
+                const int r = (int)(cc.i % TN);
+                const int s = (int)(tl % C::STAGES);
+                const int q = (int)(tl % IDX_STAGES);
+                if (G > 1) {                                              // combine the G lane groups
+#pragma unroll
+                    for (int o = LPR; o < 32; o <<= 1) {
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                        self.x += __shfl_xor_sync(0xffffffffu, self.x, o); self.y += __shfl_xor_sync(0xffffffffu, self.y, o);
+                        self.z += __shfl_xor_sync(0xffffffffu, self.z, o); self.w += __shfl_xor_sync(0xffffffffu, self.w, o);
+                    }
+                }
+                if (tl != last_tl) {                                     // first write of this warp into the stage
+                    mbar_wait(empty_bar(s), ((uint32_t)(tl / C::STAGES) & 1u) ^ 1u);
+                    last_tl = tl;
+                }
+                if (cc.valid) {
+                    const float inv = 1.0f / fmaxf(wsum, 1e-12f);
+                    const float4 mean = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+                    if (lane < LPR) {
+                        unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
+                        uint2 parts[NS];
+                        split4<NS>(self, parts);
+                        uint32_t off = b_offset(r, 4 * lane);
+#pragma unroll
+                        for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+                        split4<NS>(mean, parts);
+                        off = b_offset(r, F + 4 * lane);
+#pragma unroll
+                        for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+                    }
+                    fence_proxy_async();                                 // generic-proxy writes -> async proxy (UMMA)
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(full_bar(s));
+                    if ((cc.i + GATHER_WARPS) / TN != tl) mbar_arrive(idxe_bar(q));   // this warp's last row in the tile
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f); self = acc; wsum = 0.f;
+            }
+            advance(cc, false);
+        }
+        cp_async_wait<0>();
+    } else if (warp == LOADER_WARP) {
+        // =========================================================== edge-block loader
+        for (int64_t tl = 0;; ++tl) {
+            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
+            if (tile >= n_tiles) break;
+            const int q = (int)(tl % IDX_STAGES);
+            mbar_wait_relaxed(idxe_bar(q), ((uint32_t)(tl / IDX_STAGES) & 1u) ^ 1u);
+            const int64_t row0 = row_begin + tile * TN;
+            // rowptr[row0 .. row0+TN] (clamped to row_end), RPW words per lane
+            constexpr int RPW = (TN + 1 + 31) / 32;
+            int64_t rp[RPW];
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                int64_t rr = row0 + lane + 32 * k;
+                if (rr > row_end) rr = row_end;
+                rp[k] = (lane + 32 * k <= TN) ? (int64_t)rowptr[rr] : 0;
+            }
+            const int64_t e_lo = __shfl_sync(0xffffffffu, rp[0], 0);
+            const int64_t e_hi = __shfl_sync(0xffffffffu, rp[TN / 32], TN % 32);
+            unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
+            int32_t* rp_s = reinterpret_cast<int32_t*>(ib + EMAX * 8);
+#pragma unroll
+            for (int k = 0; k < RPW; ++k)
+                if (lane + 32 * k <= TN) rp_s[lane + 32 * k] = (int32_t)(rp[k] - e_lo);
+            if (lane == 0) *reinterpret_cast<int64_t*>(ib + EMAX * 8 + 384) = e_lo;
+            const int n = (int)((e_hi - e_lo) < EMAX ? (e_hi - e_lo) : EMAX);
+            const uint32_t cs = idx_base + (uint32_t)(q * IDX_STAGE_BYTES), ws = cs + EMAX * 4;
+            for (int k = lane; k < n; k += 32) {
+                cp_async4(cs + 4u * k, col + e_lo + k);
+                cp_async4(ws + 4u * k, ew + e_lo + k);
+            }
+            cp_async_mbar_arrive_noinc(idxf_bar(q));                     // fires when this lane's copies have landed
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
+            if (lane == 0) mbar_arrive(idxf_bar(q));                     // release: publishes the rowptr words
         }
     } else if (warp == MMA_WARP) {
         // =========================================================== MMA issuer (one thread)
@@ -312,7 +515,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             if (tile >= n_tiles) break;
             const int a = (int)(tl & 1);
             const uint32_t m = (uint32_t)(tl >> 1);
-            mbar_wait(accf_bar(a), m & 1u);
+            mbar_wait_relaxed(accf_bar(a), m & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::ACC_COL0 + a * TN);
             const int64_t row0 = row_begin + tile * TN;
