@@ -90,18 +90,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// same, with a suspend-time hint: for the roles that have slack (they should not burn issue slots spinning)
+// for the roles that have slack (epilogue, MMA issuer, loader): poll with a sleep so they do not burn
+// the issue slots the gather warps need (a tile period is ~10 us)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     uint32_t done;
-    do {
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(20000u)
+            : "r"(bar), "r"(parity)
             : "memory");
-    } while (!done);
+        if (done) break;
+        __nanosleep(400);
+    }
+}
+// predicated 16-byte async copy (no branch)
+__device__ __forceinline__ void cp_async16_pred(uint32_t smem_dst, const void* gsrc, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+        ::"r"(smem_dst), "l"(gsrc), "r"((uint32_t)pred)
+        : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
@@ -281,156 +293,196 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         // flight while the oldest is consumed (LDS + FFMA), so memory-level parallelism is bounded by the
         // ring, not by registers, and no load ever stalls a scoreboard.
         constexpr int G = 32 / LPR;                                     // items fetched by one warp instruction
+        constexpr int SLOT_FLOATS = QS * F;
         const int g = warp - GATHER_WARP0;
         const int grp = lane / LPR, sub = lane % LPR;
-        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES);
-        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_u32 - smem_base));
+        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES) + (uint32_t)((grp * F + 4 * sub) * 4);
+        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_base - smem_base) + (size_t)g * C::RING_BYTES) + grp * F + 4 * sub;
         const float* xs = x + 4 * sub;
+        const int tiles_mine = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles in this CTA's sequence
+        const int stream_end = tiles_mine * TN;
 
-        struct Cursor {
-            int64_t i;          // position in the row stream
-            int64_t tl;         // tile (in this CTA's sequence) of row i, -1 = none loaded
-            int b, nb;          // sub-batch within the row, number of sub-batches
-            int e0, deg;        // first edge (relative to the tile's e_lo) and in-degree
-            const int32_t* col_s; const float* ew_s; const int32_t* rp_s; int64_t e_lo;
-            bool valid;         // row exists (tile in range and row < row_end)
-            bool live;          // cursor still inside the CTA's tile sequence
-        };
-        auto load_row = [&](Cursor& c, bool wait_idx) {
-            const int64_t tl = c.i / TN;
-            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-            c.live = tile < n_tiles;
-            c.valid = false; c.b = 0; c.nb = 1; c.deg = 0; c.e0 = 0;
-            if (!c.live) return;
-            if (tl != c.tl) {
-                const int q = (int)(tl % IDX_STAGES);
-                if (wait_idx) mbar_wait(idxf_bar(q), (uint32_t)(tl / IDX_STAGES) & 1u);      // edge block staged
-                unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
-                c.col_s = reinterpret_cast<const int32_t*>(ib);
-                c.ew_s = reinterpret_cast<const float*>(ib + EMAX * 4);
-                c.rp_s = reinterpret_cast<const int32_t*>(ib + EMAX * 8);
-                c.e_lo = *reinterpret_cast<const int64_t*>(ib + EMAX * 8 + 384);
-                c.tl = tl;
+        // ---- per-row state, issue side (i*) and consume side (c*)
+        int ii = g, ib = 0, inb = 1, ie0 = 0, ideg = -1, itl = -1;  uint32_t irow = 0;
+        const int32_t* icol = nullptr; int64_t ielo = 0;
+        int ci = g, cb = 0, cnb = 1, ce0 = 0, cdeg = -1, ctl = -1;
+        const float* cew = nullptr; int64_t celo = 0;
+
+        auto setup_issue_row = [&]() {                                  // ii < stream_end
+            const int tl = ii / TN, r = ii % TN;
+            if (tl != itl) {
+                const int q = tl % IDX_STAGES;
+                mbar_wait(idxf_bar(q), (uint32_t)(tl / IDX_STAGES) & 1u);          // edge block staged
+                itl = tl;
             }
-            const int r = (int)(c.i % TN);
-            const int64_t row = row_begin + tile * TN + r;
+            const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
+            icol = reinterpret_cast<const int32_t*>(ibp);
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EMAX * 8);
+            ielo = *reinterpret_cast<const int64_t*>(ibp + EMAX * 8 + 384);
+            const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
+            ib = 0; inb = 1; ideg = -1;
             if (row < row_end) {
-                c.valid = true;
-                c.e0 = c.rp_s[r];
-                c.deg = c.rp_s[r + 1] - c.e0;
-                c.nb = (c.deg + 1 + QS - 1) / QS;
+                irow = (uint32_t)row;
+                ie0 = rp_s[r];
+                ideg = rp_s[r + 1] - ie0;
+                inb = (ideg + QS) / QS;                                  // ceil((deg + 1) / QS)
             }
         };
-        auto advance = [&](Cursor& c, bool wait_idx) {
-            if (++c.b < c.nb) return;
-            c.i += GATHER_WARPS;
-            load_row(c, wait_idx);
+        auto setup_consume_row = [&]() {                                // ci < stream_end, tile already staged
+            const int tl = ci / TN, r = ci % TN;
+            ctl = tl;
+            const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
+            cew = reinterpret_cast<const float*>(ibp + EMAX * 4);
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EMAX * 8);
+            celo = *reinterpret_cast<const int64_t*>(ibp + EMAX * 8 + 384);
+            const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
+            cb = 0; cnb = 1; cdeg = -1;
+            if (row < row_end) {
+                ce0 = rp_s[r];
+                cdeg = rp_s[r + 1] - ce0;
+                cnb = (cdeg + QS) / QS;
+            }
         };
-        // issue the cp.async group of the sub-batch under cursor `c` into ring slot `slot`
-        auto issue = [&](const Cursor& c, int slot) {
-            if (c.live && c.valid) {
-                const int64_t row = row_begin + ((int64_t)blockIdx.x + c.tl * gridDim.x) * TN + (c.i % TN);
+        // one cp.async group = sub-batch `ib` of the issue row, into ring slot `slot`
+        auto issue = [&](int slot) {
+            if (ii < stream_end) {
+                if (ideg >= 0) {
+                    const int first = ib * QS;
+                    const int nitems = ideg + 1 - first;                 // items left in the row (>= 1)
+                    const uint32_t dst = ring_u32 + (uint32_t)(slot * SLOT_FLOATS * 4);
+                    const int kbase = ie0 + first - 1;                   // item `it` of this sub-batch is edge kbase + it
+                    if (ie0 + ideg <= EMAX) {                            // whole row staged (the common case): branch free
+                        uint32_t src[QS / G];
 #pragma unroll
-                for (int t = 0; t < QS; t += G) {
-                    const int item = c.b * QS + t + grp;                 // 0 = self, k >= 1 = edge k-1
-                    if (item <= c.deg) {
-                        int64_t src = row;
-                        if (item > 0) {
-                            const int k = c.e0 + item - 1;
-                            src = (k < EMAX) ? c.col_s[k] : __ldg(col + c.e_lo + k);
+                        for (int t = 0; t < QS; t += G) src[t / G] = (uint32_t)icol[kbase + t + grp];   // slack reads stay in smem
+                        if (first == 0 && grp == 0) src[0] = irow;       // item 0 of the row is the self row
+#pragma unroll
+                        for (int t = 0; t < QS; t += G)
+                            cp_async16_pred(dst + (uint32_t)(t * F * 4), xs + (size_t)src[t / G] * F, t + grp < nitems);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < QS; t += G) {
+                            const int it = t + grp;
+                            if (it < nitems) {
+                                const int k = kbase + it;
+                                uint32_t src = irow;
+                                if (first + it > 0) src = (uint32_t)((k < EMAX) ? icol[k] : __ldg(col + ielo + k));
+                                cp_async16(dst + (uint32_t)(t * F * 4), xs + (size_t)src * F);
+                            }
                         }
-                        cp_async16(ring_u32 + (uint32_t)(((slot * QS + t + grp) * F + 4 * sub) * 4), xs + src * F);
                     }
+                }
+                if (++ib >= inb) {
+                    ii += GATHER_WARPS;
+                    if (ii < stream_end) setup_issue_row();
                 }
             }
             cp_async_commit();                                            // (possibly empty) group keeps the count in step
         };
 
-        Cursor ci, cc;                                                    // issue / consume cursors
-        ci.i = g; ci.tl = -1; load_row(ci, true);
-        cc = ci;
+        if (ii < stream_end) { setup_issue_row(); }
+        if (ci < stream_end) { setup_consume_row(); }
         int islot = 0, cslot = 0;
 #pragma unroll
-        for (int d = 0; d < NQ - 1; ++d) {                               // prologue: NQ-1 groups in flight
-            issue(ci, islot);
-            islot = (islot + 1) % NQ;
-            if (ci.live) advance(ci, true);
-        }
+        for (int d = 0; d < NQ - 1; ++d) { issue(islot); islot = (islot + 1) % NQ; }   // prologue: NQ-1 groups in flight
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), self = acc;
         float wsum = 0.f;
-        int64_t last_tl = -1;
-        while (cc.live) {
+        int last_tl = -1;
+        while (ci < stream_end) {
             cp_async_wait<NQ - 2>();                                      // oldest group landed (this lane's part) ...
-            __syncwarp();                                                 // ... and everyone else's
-            if (cc.valid) {
+            __syncwarp();                                                 // ... and everyone else's; also: all lanes are
+                                                                          // done reading the slot consumed last iteration
+            issue(islot);                                                 // refill that slot
+            islot = (islot + 1) % NQ;
+            if (cdeg >= 0) {
+                const int first = cb * QS;
+                const int nitems = cdeg + 1 - first;
+                const float* rs = ring_gen + cslot * SLOT_FLOATS;
+                const int kbase = ce0 + first - 1;
+                if (ce0 + cdeg <= EMAX) {                                // whole row staged: batched LDS, predicated math
+                    float4 v[QS / G];
+                    float w[QS / G];
 #pragma unroll
-                for (int t = 0; t < QS; t += G) {
-                    const int item = cc.b * QS + t + grp;
-                    if (item <= cc.deg) {
-                        const float4 v = *reinterpret_cast<const float4*>(ring_gen + ((cslot * QS + t + grp) * F + 4 * sub));
-                        if (item == 0) {
-                            self = v;
-                        } else {
-                            const int k = cc.e0 + item - 1;
-                            const float w = (k < EMAX) ? cc.ew_s[k] : __ldg(ew + cc.e_lo + k);
-                            wsum += w;
-                            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    for (int t = 0; t < QS; t += G) {
+                        v[t / G] = *reinterpret_cast<const float4*>(rs + t * F);
+                        w[t / G] = cew[kbase + t + grp];
+                    }
+                    if (first == 0 && grp == 0) { self = v[0]; w[0] = 0.f; v[0] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                    for (int t = 0; t < QS; t += G) {
+                        if (t + grp < nitems) {
+                            const float wt = w[t / G];
+                            const float4 vt = v[t / G];
+                            wsum += wt;
+                            acc.x = fmaf(wt, vt.x, acc.x); acc.y = fmaf(wt, vt.y, acc.y);
+                            acc.z = fmaf(wt, vt.z, acc.z); acc.w = fmaf(wt, vt.w, acc.w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < QS; t += G) {
+                        const int it = t + grp;
+                        if (it < nitems) {
+                            const float4 v = *reinterpret_cast<const float4*>(rs + t * F);
+                            if (t == 0 && first + it == 0) {
+                                self = v;
+                            } else {
+                                const int k = kbase + it;
+                                const float w = (k < EMAX) ? cew[k] : __ldg(ew + celo + k);
+                                wsum += w;
+                                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                            }
                         }
                     }
                 }
             }
-            __syncwarp();                                                 // slot fully read before it is refilled
-            issue(ci, islot);                                             // refill the ring
-            islot = (islot + 1) % NQ;
-            if (ci.live) advance(ci, true);
             cslot = (cslot + 1) % NQ;
+            if (++cb < cnb) continue;
 
-            if (cc.b + 1 == cc.nb) {
-                // ---- row complete: normalise, split to bf16 terms, write the UMMA B operand, signal
-                const int64_t tl = cc.tl;
-                const int r = (int)(cc.i % TN);
-                const int s = (int)(tl % C::STAGES);
-                const int q = (int)(tl % IDX_STAGES);
-                if (G > 1) {                                              // combine the G lane groups
+            // ---- row complete: normalise, split to bf16 terms, write the UMMA B operand, signal
+            const int tl = ctl;
+            const int r = ci % TN;
+            const int s = tl % C::STAGES;
+            if (G > 1) {                                                  // combine the G lane groups
 #pragma unroll
-                    for (int o = LPR; o < 32; o <<= 1) {
-                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-                        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-                        self.x += __shfl_xor_sync(0xffffffffu, self.x, o); self.y += __shfl_xor_sync(0xffffffffu, self.y, o);
-                        self.z += __shfl_xor_sync(0xffffffffu, self.z, o); self.w += __shfl_xor_sync(0xffffffffu, self.w, o);
-                    }
+                for (int o = LPR; o < 32; o <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                    self.x += __shfl_xor_sync(0xffffffffu, self.x, o); self.y += __shfl_xor_sync(0xffffffffu, self.y, o);
+                    self.z += __shfl_xor_sync(0xffffffffu, self.z, o); self.w += __shfl_xor_sync(0xffffffffu, self.w, o);
                 }
-                if (tl != last_tl) {                                     // first write of this warp into the stage
-                    mbar_wait(empty_bar(s), ((uint32_t)(tl / C::STAGES) & 1u) ^ 1u);
-                    last_tl = tl;
-                }
-                if (cc.valid) {
-                    const float inv = 1.0f / fmaxf(wsum, 1e-12f);
-                    const float4 mean = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-                    if (lane < LPR) {
-                        unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
-                        uint2 parts[NS];
-                        split4<NS>(self, parts);
-                        uint32_t off = b_offset(r, 4 * lane);
+            }
+            if (tl != last_tl) {                                         // first write of this warp into the stage
+                mbar_wait(empty_bar(s), ((uint32_t)(tl / C::STAGES) & 1u) ^ 1u);
+                last_tl = tl;
+            }
+            if (cdeg >= 0) {
+                const float inv = 1.0f / fmaxf(wsum, 1e-12f);
+                const float4 mean = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+                if (lane < LPR) {
+                    unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
+                    uint2 parts[NS];
+                    split4<NS>(self, parts);
+                    uint32_t off = b_offset(r, 4 * lane);
 #pragma unroll
-                        for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
-                        split4<NS>(mean, parts);
-                        off = b_offset(r, F + 4 * lane);
+                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+                    split4<NS>(mean, parts);
+                    off = b_offset(r, F + 4 * lane);
 #pragma unroll
-                        for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
-                    }
-                    fence_proxy_async();                                 // generic-proxy writes -> async proxy (UMMA)
+                    for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(full_bar(s));
-                    if ((cc.i + GATHER_WARPS) / TN != tl) mbar_arrive(idxe_bar(q));   // this warp's last row in the tile
-                }
+                fence_proxy_async();                                     // generic-proxy writes -> async proxy (UMMA)
                 acc = make_float4(0.f, 0.f, 0.f, 0.f); self = acc; wsum = 0.f;
             }
-            advance(cc, false);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(full_bar(s));
+                if ((ci + GATHER_WARPS) / TN != tl) mbar_arrive(idxe_bar(tl % IDX_STAGES));   // this warp's last row in the tile
+            }
+            ci += GATHER_WARPS;
+            if (ci < stream_end) setup_consume_row();
         }
         cp_async_wait<0>();
     } else if (warp == LOADER_WARP) {
@@ -479,8 +531,8 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 const uint32_t n = (uint32_t)(tl / C::STAGES);
                 const int a = (int)(tl & 1);
                 const uint32_t m = (uint32_t)(tl >> 1);
-                mbar_wait(acce_bar(a), (m & 1u) ^ 1u);                   // epilogue drained this accumulator
-                mbar_wait(full_bar(s), n & 1u);                          // gather filled this stage
+                mbar_wait_relaxed(acce_bar(a), (m & 1u) ^ 1u);           // epilogue drained this accumulator
+                mbar_wait_relaxed(full_bar(s), n & 1u);                  // gather filled this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(C::ACC_COL0 + a * TN);
                 const uint32_t st0 = smem_base + (uint32_t)(s * C::STAGE_BYTES);
