@@ -67,6 +67,14 @@ int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowptr_is64, co
                          int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
                          int relu, int algo, nerrf_stream_t stream);
 
+/* The same layer with the node head fused into its epilogue (used for the last layer):
+ * additionally score[v] = sigmoid(out_v . node_w + node_b) for v in [row_begin,row_end). */
+int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                              const float* ew, const float* W, const float* b, float* out,
+                              int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
+                              int relu, int algo, const float* node_w, float node_b, float* score,
+                              nerrf_stream_t stream);
+
 /* Heads.  score[v] = sigmoid(h_v . node_w + node_b).  If edge_W != NULL also writes
  * proj[v] = (h_v.We[0:H,0], h_v.We[0:H,1], h_v.We[H:2H,0], h_v.We[H:2H,1])  (proj [n,4]). */
 int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,

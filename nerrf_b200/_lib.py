@@ -26,6 +26,8 @@ SIGNATURES = {
     "nerrf_sage_aggregate": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp]),
     "nerrf_sage_layer_fwd": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "nerrf_sage_layer_head_fwd": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp]),
     "nerrf_sage_node_head": (C.c_int, [vp, vp, C.c_float, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "nerrf_sage_edge_head": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, vp]),
     "nerrf_sage_forward": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int,

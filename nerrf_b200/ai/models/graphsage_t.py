@@ -94,17 +94,21 @@ class GraphSAGE_T(nn.Module):
                 raise ValueError("graph tensors must be contiguous")
 
     # -- single layer (used by the sharded forward) ---------------------------------------
-    def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True):
+    def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None):
+        """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue."""
         self._check_graph(h, rowptr, col, edge_w)
         N = h.shape[0]
         row_end = N if row_end is None else row_end
         if out is None:
             out = torch.empty(N, self.hidden, device=h.device, dtype=torch.float32)
         W, b = self.weights[l], self.biases[l]
-        L.check(L.lib().nerrf_sage_layer_fwd(L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col),
-                                             L.ptr(edge_w), L.ptr(W), L.ptr(b), L.ptr(out), N, row_begin, row_end,
-                                             h.shape[1], self.hidden, int(relu), ALGOS[self.algo],
-                                             L.current_stream_ptr()), "nerrf_sage_layer_fwd")
+        args = (L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col), L.ptr(edge_w), L.ptr(W), L.ptr(b),
+                L.ptr(out), N, row_begin, row_end, h.shape[1], self.hidden, int(relu), ALGOS[self.algo])
+        if score_out is None:
+            L.check(L.lib().nerrf_sage_layer_fwd(*args, L.current_stream_ptr()), "nerrf_sage_layer_fwd")
+        else:
+            L.check(L.lib().nerrf_sage_layer_head_fwd(*args, L.ptr(self.node_w), self._node_b_host(), L.ptr(score_out),
+                                                      L.current_stream_ptr()), "nerrf_sage_layer_head_fwd")
         return out
 
     def heads(self, h, rowptr, col, return_edge_logits=False, row_begin=0, row_end=None):

@@ -12,7 +12,8 @@ namespace nerrf {
 
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew,
                     const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin,
-                    int64_t row_end, int F, int relu, int nsplit, cudaStream_t st);   // sage_umma.cu
+                    int64_t row_end, int F, int relu, int nsplit, const float* node_w, float node_b, float* score,
+                    cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
 bool sage_umma_available();
 
 // ------------------------------------------------------------------------------------------
@@ -276,10 +277,10 @@ extern "C" int nerrf_sage_aggregate(const float* x, const void* rowptr, int rowp
     return launch_status("sage_aggregate_kernel");
 }
 
-extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
-                                    const float* ew, const float* W, const float* b, float* out, int64_t n_nodes,
-                                    int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
-                                    nerrf_stream_t stream) {
+static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col, const float* ew,
+                          const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end,
+                          int F, int H, int relu, int algo, const float* node_w, float node_b, float* score,
+                          nerrf_stream_t stream) {
     int rc = check_graph_args(x, rowptr, col, ew, n_nodes, row_begin, row_end);
     if (rc) return rc;
     NERRF_REQUIRE(W && b && out, "null weight/output pointer");
@@ -287,15 +288,35 @@ extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowp
     NERRF_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)b & 15) == 0,
                   "out/W/b must be 16-byte aligned");
     NERRF_REQUIRE(x != out, "in-place layer is not supported");
+    NERRF_REQUIRE(!node_w || score, "score output required with node_w");
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo == NERRF_SAGE_ALGO_AUTO) algo = sage_umma_available() && (F == 32 || F == 128) ? NERRF_SAGE_ALGO_UMMA : NERRF_SAGE_ALGO_FFMA;
+    if (algo == NERRF_SAGE_ALGO_AUTO) algo = sage_umma_available() ? NERRF_SAGE_ALGO_UMMA : NERRF_SAGE_ALGO_FFMA;
     if (algo == NERRF_SAGE_ALGO_UMMA || algo == NERRF_SAGE_ALGO_UMMA2)
         return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu,
-                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, st);
+                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, st);
     NERRF_REQUIRE(algo == NERRF_SAGE_ALGO_FFMA, "unknown algo %d", algo);
-    if (rowptr_is64)
-        return layer_dispatch<int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st);
-    return layer_dispatch<int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st);
+    rc = rowptr_is64
+             ? layer_dispatch<int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st)
+             : layer_dispatch<int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st);
+    if (rc || !node_w) return rc;
+    return nerrf_sage_node_head(out, node_w, node_b, score, nullptr, nullptr, row_begin, row_end, H, stream);
+}
+
+extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                                    const float* ew, const float* W, const float* b, float* out, int64_t n_nodes,
+                                    int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
+                                    nerrf_stream_t stream) {
+    return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo,
+                          nullptr, 0.f, nullptr, stream);
+}
+
+extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                                         const float* ew, const float* W, const float* b, float* out, int64_t n_nodes,
+                                         int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
+                                         const float* node_w, float node_b, float* score, nerrf_stream_t stream) {
+    NERRF_REQUIRE(node_w && score, "null head pointer");
+    return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
+                          node_b, score, stream);
 }
 
 extern "C" int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,
@@ -342,20 +363,18 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
             return NERRF_ERR_WORKSPACE;
         }
     }
+    if (score_out) NERRF_REQUIRE(node_w, "node_w required for score_out");
     const float* in = x;
     int F = f_in;
     for (int l = 0; l < num_layers; ++l) {
         float* o = ((num_layers - 1 - l) % 2 == 0) ? h_out : workspace;
-        int rc = nerrf_sage_layer_fwd(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1,
-                                      algo, stream);
+        const bool last = l == num_layers - 1;
+        int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1, algo,
+                                (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
+                                stream);
         if (rc) return rc;
         in = o;
         F = hidden;
-    }
-    if (score_out) {
-        NERRF_REQUIRE(node_w, "node_w required for score_out");
-        int rc = nerrf_sage_node_head(h_out, node_w, node_b, score_out, nullptr, nullptr, 0, n_nodes, hidden, stream);
-        if (rc) return rc;
     }
     return NERRF_OK;
 }

@@ -20,7 +20,8 @@
 //   warps 0-3   epilogue: tcgen05.ld accumulator (lane = feature), + bias, ReLU, 128 B/warp stores
 //   warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma, commit -> mbarriers)
 //   warp  5     edge-block loader: stages each tile's rowptr / col / ew slice into shared memory with
-//               cp.async (completion on an mbarrier), running up to IDX_STAGES tiles ahead
+//               cp.async (completion on an mbarrier), running up to IDX_STAGES tiles ahead; the next tile's
+//               rowptr words are prefetched before it waits for a free stage
 //   warps 6-15  gather: one CSR row per warp at a time (sage_gather.cuh), rows round-robin; indices
 //               come from shared memory, so the only global latency a row exposes is its x rows
 // Pipelines: idx stages full/empty (loader <-> gather), smem operand stages full/empty (gather <-> MMA),
@@ -39,12 +40,10 @@ constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
 constexpr int LOADER_WARP = 5;
 constexpr int GATHER_WARP0 = 6;
-constexpr int GATHER_WARPS = 14;
-constexpr int UMMA_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 640
-constexpr int IDX_STAGES = 3;
 constexpr int EMAX = 512;              // staged edges per tile (4 KB); the rest of a heavier tile is read from global
 constexpr int IDX_STAGE_BYTES = EMAX * 8 + 512;      // col[EMAX] | ew[EMAX] | rp[TN+1] (relative) | e_lo (int64)
-constexpr int QS = 4;                  // items (source rows) per sub-batch = one cp.async group
+// items (source rows) per sub-batch (= one cp.async group): 4 warp-wide copy instructions, i.e. 4 * (32 / (F/4))
+template <int F> constexpr int qs_for() { return 4 * (32 / (F / 4)); }
 constexpr int NQ = 4;                  // sub-batch slots in a warp's ring; NQ-1 groups are in flight
 
 // NS = number of bf16 terms each fp32 value is split into (v = p0 + p1 [+ p2], p_i = bf16 of the
@@ -52,18 +51,22 @@ constexpr int NQ = 4;                  // sub-batch slots in a warp's ring; NQ-1
 // terms below 2^-24: fp32-equivalent.  NS = 2 with three products is ~1e-5 relative.
 template <int F, int NS>
 struct UmmaCfg {
+    static constexpr int GATHER_WARPS = (F == 32) ? 18 : 14;  // F=32 leaves room for more rings (and needs more TLP)
+    static constexpr int THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;
+    static constexpr int IDX_STAGES = (F == 32) ? 4 : 3;
     static constexpr int K = 2 * F;
     static constexpr int KB = K / 64;                        // 128-byte K blocks
     static constexpr int KSTEPS = K / 16;                    // MMAs (K=16) per product
     static constexpr int PART_BYTES = KB * TN * 128;         // one bf16 term of one stage
     static constexpr int STAGE_BYTES = NS * PART_BYTES;
+    static constexpr int QS = qs_for<F>();                    // 4 (F=128), 8 (F=64), 16 (F=32): always 2 KB per sub-batch
     static constexpr int RING_BYTES = NQ * QS * F * 4;       // per gather warp: NQ sub-batches x QS source rows
     static constexpr int STAGES = (F == 128) ? 2 : 4;
     static constexpr int W_PART_COLS = K / 2;                // W^T term p lives in TMEM columns [p*K/2, (p+1)*K/2)
     static constexpr int ACC_COL0 = NS * W_PART_COLS;
     static constexpr int TMEM_COLS = (ACC_COL0 + 2 * TN <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + IDX_STAGES * IDX_STAGE_BYTES +
-                                   (size_t)GATHER_WARPS * RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+                                   (size_t)GATHER_WARPS * RING_BYTES + 1024 /*head reduce*/ + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least two smem stages");
     static_assert(ACC_COL0 + 2 * TN <= 512, "TMEM overflow");
@@ -209,6 +212,22 @@ __device__ __forceinline__ void split4(const float4 v, uint2 (&parts)[NS]) {
     for (int p = 0; p < NS; ++p) parts[p] = make_uint2(lo[p], hi[p]);
 }
 
+// v[j] (j = 0..31) per lane  ->  sum over the 32 lanes of v[lane]: a 32x32 transpose-reduce in 31 shuffles
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int n = 16 >> s;                                  // also the xor offset
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? v[i] : v[i + n];
+            const float keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+
 // byte offset of element (row r, k) inside one hi/lo part of a stage (k multiple of 4)
 __device__ __forceinline__ uint32_t b_offset(int r, int k) {
     const int kb = k >> 6, col = k & 63;
@@ -217,12 +236,14 @@ __device__ __forceinline__ uint32_t b_offset(int r, int k) {
 }
 
 template <int F, int NS, typename RP>
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
+__global__ void __launch_bounds__((UmmaCfg<F, NS>::THREADS), 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
-                       float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu) {
+                       float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu,
+                       const float* __restrict__ node_w, float node_b, float* __restrict__ score) {
     using C = UmmaCfg<F, NS>;
     constexpr int K = C::K, LPR = F / 4;
+    constexpr int GATHER_WARPS = C::GATHER_WARPS, IDX_STAGES = C::IDX_STAGES;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
     unsigned char* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -237,6 +258,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4 + 2 * IDX_STAGES);
     unsigned char* idx_gen = smem_gen + (idx_base - smem_base);
     const uint32_t ring_base = bar_base + 256;
+    float* head_red = reinterpret_cast<float*>(smem_gen + (ring_base - smem_base) + (size_t)GATHER_WARPS * C::RING_BYTES);   // [2][4][32]
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -293,6 +315,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         // flight while the oldest is consumed (LDS + FFMA), so memory-level parallelism is bounded by the
         // ring, not by registers, and no load ever stalls a scoreboard.
         constexpr int G = 32 / LPR;                                     // items fetched by one warp instruction
+        constexpr int QS = C::QS;
         constexpr int SLOT_FLOATS = QS * F;
         const int g = warp - GATHER_WARP0;
         const int grp = lane / LPR, sub = lane % LPR;
@@ -487,21 +510,25 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         cp_async_wait<0>();
     } else if (warp == LOADER_WARP) {
         // =========================================================== edge-block loader
-        for (int64_t tl = 0;; ++tl) {
-            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-            if (tile >= n_tiles) break;
-            const int q = (int)(tl % IDX_STAGES);
-            mbar_wait_relaxed(idxe_bar(q), ((uint32_t)(tl / IDX_STAGES) & 1u) ^ 1u);
+        constexpr int RPW = (TN + 1 + 31) / 32;
+        auto load_rp = [&](int64_t tile, int64_t (&rp)[RPW]) {          // rowptr[row0 .. row0+TN], clamped to row_end
             const int64_t row0 = row_begin + tile * TN;
-            // rowptr[row0 .. row0+TN] (clamped to row_end), RPW words per lane
-            constexpr int RPW = (TN + 1 + 31) / 32;
-            int64_t rp[RPW];
 #pragma unroll
             for (int k = 0; k < RPW; ++k) {
                 int64_t rr = row0 + lane + 32 * k;
                 if (rr > row_end) rr = row_end;
                 rp[k] = (lane + 32 * k <= TN) ? (int64_t)rowptr[rr] : 0;
             }
+        };
+        int64_t rp[RPW], rp_next[RPW];
+        if ((int64_t)blockIdx.x < n_tiles) load_rp(blockIdx.x, rp);
+        for (int64_t tl = 0;; ++tl) {
+            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
+            if (tile >= n_tiles) break;
+            const bool has_next = tile + gridDim.x < n_tiles;
+            if (has_next) load_rp(tile + gridDim.x, rp_next);           // in flight while we wait for a free stage
+            const int q = (int)(tl % IDX_STAGES);
+            mbar_wait_relaxed(idxe_bar(q), ((uint32_t)(tl / IDX_STAGES) & 1u) ^ 1u);
             const int64_t e_lo = __shfl_sync(0xffffffffu, rp[0], 0);
             const int64_t e_hi = __shfl_sync(0xffffffffu, rp[TN / 32], TN % 32);
             unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
@@ -519,6 +546,8 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             cp_async_mbar_arrive_noinc(idxf_bar(q));                     // fires when this lane's copies have landed
             __syncwarp();
             if (lane == 0) mbar_arrive(idxf_bar(q));                     // release: publishes the rowptr words
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) rp[k] = rp_next[k];
         }
     } else if (warp == MMA_WARP) {
         // =========================================================== MMA issuer (one thread)
@@ -562,6 +591,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     } else {
         // =========================================================== epilogue warps
         const int f = warp * 32 + lane;
+        const float my_nw = node_w ? __ldg(node_w + f) : 0.f;
         for (int64_t tl = 0;; ++tl) {
             const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
             if (tile >= n_tiles) break;
@@ -571,21 +601,30 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::ACC_COL0 + a * TN);
             const int64_t row0 = row_begin + tile * TN;
+            uint32_t v[32];
+            tmem_ld32(taddr, v);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(acce_bar(a));                                    // accumulator drained: the MMA may reuse it
+            float hv[32];
 #pragma unroll
-            for (int half = 0; half < TN / 32; ++half) {
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)(half * 32), v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t row = row0 + half * 32 + j;
-                    float o = __uint_as_float(v[j]) + my_bias;
-                    if (relu) o = fmaxf(o, 0.f);
-                    if (row < row_end) out[row * UM + f] = o;
+            for (int j = 0; j < 32; ++j) {
+                float o = __uint_as_float(v[j]) + my_bias;
+                if (relu) o = fmaxf(o, 0.f);
+                if (row0 + j < row_end) out[(row0 + j) * UM + f] = o;
+                hv[j] = o * my_nw;
+            }
+            if (node_w) {
+                // fused node head: score[row] = sigmoid(h[row,:] . node_w + node_b)
+                const float part = warp_transpose_reduce32(hv, lane);    // lane l: this warp's 32 features of row l
+                head_red[(a * EPI_WARPS + warp) * 32 + lane] = part;
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+                if (warp == 0) {
+                    const float* hr = head_red + a * EPI_WARPS * 32 + lane;
+                    const float dot = (hr[0] + hr[32]) + (hr[64] + hr[96]);
+                    if (row0 + lane < row_end) score[row0 + lane] = 1.f / (1.f + expf(-(dot + node_b)));
                 }
             }
-            tc_fence_before();
-            mbar_arrive(acce_bar(a));
         }
     }
 
@@ -599,7 +638,8 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
-                float* out, int64_t row_begin, int64_t row_end, int relu, cudaStream_t st) {
+                float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
+                cudaStream_t st) {
     using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -610,7 +650,7 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     const int64_t tiles = (rows + TN - 1) / TN;
     if (tiles == 0) return NERRF_OK;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, UMMA_THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu);
+    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score);
     return launch_status("sage_layer_umma_kernel");
 }
 
@@ -620,11 +660,11 @@ bool sage_umma_available() { return true; }
 
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
-                    int nsplit, cudaStream_t st) {
+                    int nsplit, const float* node_w, float node_b, float* score, cudaStream_t st) {
     (void)n_nodes;
-#define GO(FV, NSV)                                                                                                          \
-    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st) \
-                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, st)
+#define GO(FV, NSV)                                                                                                                                   \
+    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, st) \
+                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, st)
     if (nsplit == 3) {
         switch (F) {
             case 32: GO(32, 3);

@@ -162,3 +162,18 @@ def test_full_size_properties():
     want = S.layer(h2_.cpu(), torch.from_numpy(g.rowptr), torch.from_numpy(g.col), torch.from_numpy(g.ew), W, b,
                    row_begin=500000, row_end=500256)
     assert_close_fp32(h[500000:500256], want, what="full-size layer-3 rows")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fused_head_matches_separate_head(algo):
+    g = G.synthetic_graph(N=7001, E=80000, seed=4, f_in=128)
+    model = GraphSAGE_T(128, 128, 1, algo=algo).cuda()
+    x, rp, col, ew = dev_graph(g)
+    score = torch.full((7001,), -1.0, device="cuda")
+    h = model.layer_forward(0, x, rp, col, ew, score_out=score)
+    sep, _ = model.heads(h, rp, col)
+    assert (score - sep).abs().max() < 1e-6
+    # row range: scores outside [row_begin,row_end) untouched
+    score2 = torch.full((7001,), -1.0, device="cuda")
+    model.layer_forward(0, x, rp, col, ew, row_begin=100, row_end=6000, score_out=score2)
+    assert torch.equal(score2[100:6000], score[100:6000]) and (score2[:100] == -1).all() and (score2[6000:] == -1).all()
