@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:       # NVML missing: report it rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -313,6 +313,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "umma", "umma2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="broadcast", choices=["broadcast", "allreduce"],
+                    help="N>1: per-layer embedding exchange (all-gather-v by broadcasts, or the all-reduce contract)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

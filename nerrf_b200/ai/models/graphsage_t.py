@@ -94,15 +94,23 @@ class GraphSAGE_T(nn.Module):
                 raise ValueError("graph tensors must be contiguous")
 
     # -- single layer (used by the sharded forward) ---------------------------------------
-    def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None):
-        """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue."""
+    def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None,
+                      edge_base: int = 0):
+        """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue.
+        edge_base: `col` / `edge_w` hold only the edge block [edge_base, edge_base + len) of the graph (a
+        1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data."""
         self._check_graph(h, rowptr, col, edge_w)
         N = h.shape[0]
         row_end = N if row_end is None else row_end
         if out is None:
             out = torch.empty(N, self.hidden, device=h.device, dtype=torch.float32)
         W, b = self.weights[l], self.biases[l]
-        args = (L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col), L.ptr(edge_w), L.ptr(W), L.ptr(b),
+        if edge_base:
+            import ctypes as C
+            colp = C.c_void_p(col.data_ptr() - 4 * edge_base); ewp = C.c_void_p(edge_w.data_ptr() - 4 * edge_base)
+        else:
+            colp, ewp = L.ptr(col), L.ptr(edge_w)
+        args = (L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b),
                 L.ptr(out), N, row_begin, row_end, h.shape[1], self.hidden, int(relu), ALGOS[self.algo])
         if score_out is None:
             L.check(L.lib().nerrf_sage_layer_fwd(*args, L.current_stream_ptr()), "nerrf_sage_layer_fwd")

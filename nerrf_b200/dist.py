@@ -1,0 +1,215 @@
+"""Multi-GPU paths: one process per GPU, torch.distributed for the plumbing.
+
+GraphSAGE-T   1-D EDGE-BLOCK shards over the CSR-by-destination edge array with ROW-ALIGNED cuts
+              (graph.edge_balanced_row_cuts): rank g owns destination rows [cuts[g], cuts[g+1]) and
+              therefore the contiguous edge block [rowptr[cuts[g]], rowptr[cuts[g+1]]).  Every rank
+              keeps the full node-embedding matrix of the current layer; after each layer the ranks
+              exchange the rows they produced (one collective per layer):
+                exchange="broadcast"  all-gather-v as one broadcast per owner (half the traffic of an
+                                      all-reduce, no fp32 re-association) -- default
+                exchange="allreduce"  the north star's contract: zero outside the owned rows, SUM
+              The last layer's node scores stay sharded (each rank returns its rows).
+MCTS          root parallelism, no collective on the data path: rank g runs an independent tree with
+              seed + g; the [A]-sized root statistics are summed in rank order afterwards.
+
+The compute is injected (`layer_fn`), so the same sharding / exchange logic runs on CPU under gloo
+in tests (with the oracle as the layer) and on GPUs under NCCL (with the CUDA kernels).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import graph as G
+
+
+class Shard:
+    """What one rank holds: full rowptr, its edge block of col / ew (indexed from edge_base)."""
+
+    def __init__(self, rowptr, col, ew, rank, world, device=None):
+        rp = rowptr.cpu().numpy() if isinstance(rowptr, torch.Tensor) else np.asarray(rowptr)
+        self.cuts = G.edge_balanced_row_cuts(rp, world)
+        self.rank, self.world = rank, world
+        self.row_begin, self.row_end = int(self.cuts[rank]), int(self.cuts[rank + 1])
+        self.edge_base, self.edge_end = int(rp[self.row_begin]), int(rp[self.row_end])
+        dev = device or (rowptr.device if isinstance(rowptr, torch.Tensor) else "cpu")
+        t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+        self.rowptr = t(rowptr).to(dev)
+        self.col = t(col)[self.edge_base:self.edge_end].contiguous().to(dev)
+        self.ew = t(ew)[self.edge_base:self.edge_end].contiguous().to(dev)
+        self.num_nodes = self.rowptr.numel() - 1
+
+
+def exchange_rows(buf, cuts, rank, world, mode="broadcast", group=None):
+    """After a layer: every rank has written buf[cuts[rank]:cuts[rank+1]]; make buf complete everywhere."""
+    if world == 1:
+        return
+    if mode == "allreduce":
+        rb, re = int(cuts[rank]), int(cuts[rank + 1])
+        buf[:rb].zero_(); buf[re:].zero_()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        return
+    works = []
+    for g in range(world):
+        rb, re = int(cuts[g]), int(cuts[g + 1])
+        if re > rb:
+            works.append(dist.broadcast(buf[rb:re], src=g, group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+def sharded_forward(layer_fn, num_layers, x, shard: Shard, hidden, bufs=None, exchange="broadcast", group=None,
+                    head_fn=None):
+    """layer_fn(l, h_in, out, shard) must write out[shard.row_begin:shard.row_end] for layer l.
+    Returns (h_full, head_fn(h_full, shard) or None)."""
+    N = x.shape[0]
+    if bufs is None:
+        bufs = [torch.empty(N, hidden, dtype=x.dtype, device=x.device) for _ in range(min(2, num_layers))]
+    h = x
+    for l in range(num_layers):
+        out = bufs[l % len(bufs)]
+        layer_fn(l, h, out, shard)
+        exchange_rows(out, shard.cuts, shard.rank, shard.world, exchange, group)
+        h = out
+    return h, (head_fn(h, shard) if head_fn is not None else None)
+
+
+def root_parallel_search(search_fn, rank, world, group=None):
+    """search_fn(seed_offset) -> (root_n int32 [A], root_w fp32 [A]).  Returns merged (n, w) on every rank;
+    the fp32 sums are accumulated in rank order so every rank gets bit-identical statistics."""
+    n, w = search_fn(rank)
+    n = torch.as_tensor(np.asarray(n)).clone(); w = torch.as_tensor(np.asarray(w)).clone()
+    if world == 1:
+        return n.numpy(), w.numpy()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    ns = [torch.empty_like(n, device=dev) for _ in range(world)]
+    ws = [torch.empty_like(w, device=dev) for _ in range(world)]
+    dist.all_gather(ns, n.to(dev), group=group)
+    dist.all_gather(ws, w.to(dev), group=group)
+    tot_n = torch.zeros_like(ns[0]); tot_w = torch.zeros_like(ws[0])
+    for g in range(world):
+        tot_n += ns[g]
+        tot_w = tot_w + ws[g]
+    return tot_n.cpu().numpy(), tot_w.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------- GPU side
+def gpu_synthetic_graph(N, E, seed, device):
+    """Same distribution as graph.synthetic_graph (dst ~ U, src = floor(N u^3), t ~ U[0,60), conf ~ U[.5,1]),
+    generated on the GPU so every rank can build the N x 10M-edge graph in about a second.  The CUDA Philox
+    generator is deterministic per (seed, call order), so all ranks hold the same graph."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    dst = torch.randint(0, N, (E,), generator=gen, device=device, dtype=torch.int64)
+    src = (N * torch.rand(E, generator=gen, device=device, dtype=torch.float64) ** 3).long().clamp_(max=N - 1)
+    t = torch.rand(E, generator=gen, device=device) * G.WINDOW
+    conf = 0.5 + 0.5 * torch.rand(E, generator=gen, device=device)
+    order = torch.argsort(t, stable=True)
+    order = order[torch.argsort(dst[order], stable=True)]
+    src, dst, t, conf = src[order], dst[order], t[order], conf[order]
+    counts = torch.bincount(dst, minlength=N)
+    rowptr = torch.zeros(N + 1, dtype=torch.int32 if E < 2 ** 31 else torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    ew = conf * torch.exp(-(G.WINDOW - t) / G.TAU)
+    x = torch.randn(N, G.F_IN, generator=torch.Generator(device=device).manual_seed(seed + 1), device=device)
+    return rowptr, src.to(torch.int32), ew.float().contiguous(), x
+
+
+def cuda_layer_fn(model):
+    """layer_fn for sharded_forward backed by the CUDA kernels (edge block addressed via edge_base)."""
+    def fn(l, h, out, shard, score_out=None):
+        model.layer_forward(l, h, shard.rowptr, shard.col, shard.ew, out=out, row_begin=shard.row_begin,
+                            row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out)
+    return fn
+
+
+def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, algorithmic_bytes_layer, measured_peaks,
+                  ClockSampler, physical_gpu_index, run_mcts_bench):
+    """bench.py's N > 1 arm (weak scaling: N x (1M nodes, 10M edges), one exchange per layer)."""
+    from bench import N_NODES, N_EDGES, HIDDEN, LAYERS, F_IN
+    N, E = N_NODES * world, N_EDGES * world
+    rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev)
+    shard = Shard(rowptr, col, ew, rank, world, device=dev)
+    del col, ew
+    torch.cuda.empty_cache()
+    bufs = [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
+    score = torch.empty(N, device=dev)
+    layer = cuda_layer_fn(model)
+    K, W = args.steps, max(args.warmup, 3)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * LAYERS + 1)] for _ in range(K)]
+
+    def step(i=None):
+        h = x
+        if i is not None: ev[i][0].record()
+        for l in range(LAYERS):
+            out = bufs[l & 1]
+            last = l == LAYERS - 1
+            layer(l, h, out, shard, score_out=score if last else None)
+            if i is not None: ev[i][2 * l + 1].record()
+            if not last:                                    # the last layer's rows / scores stay sharded
+                exchange_rows(out, shard.cuts, rank, world, args.exchange)
+            if i is not None: ev[i][2 * l + 2].record()
+            h = out
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize(); dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank)); sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for i in range(K):
+        step(i)
+    t1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    clocks = sampler.result()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / K
+    seg = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(2 * LAYERS)] for i in range(K)]).mean(0)
+    comp_ms, comm_ms = seg[0::2], seg[1::2]
+    peak, peak_src = measured_peaks()
+    e_loc, r_loc = shard.edge_end - shard.edge_base, shard.row_end - shard.row_begin
+    dom_bytes = algorithmic_bytes_layer(e_loc, r_loc, HIDDEN)
+    dom_ms = float(comp_ms[1])
+    mcts_local = run_mcts_bench(dev, args, seed=rank)
+    roll = torch.tensor([mcts_local["value"]], device=dev)
+    dist.all_reduce(roll, op=dist.ReduceOp.SUM)
+    mcts_local.update({"value": float(roll), "note": "root-parallel: sum over ranks of independent trees (seed = rank), no collective"})
+    # ---- e2e: the same sharded step with this rank's inputs coming from pinned host memory every step
+    hx, hrp, hcol, hew = (t.cpu().pin_memory() for t in (x, shard.rowptr, shard.col, shard.ew))
+    hscore = torch.empty(r_loc).pin_memory()
+    def e2e_step():
+        x.copy_(hx, non_blocking=True); shard.rowptr.copy_(hrp, non_blocking=True)
+        shard.col.copy_(hcol, non_blocking=True); shard.ew.copy_(hew, non_blocking=True)
+        step()
+        hscore.copy_(score[shard.row_begin:shard.row_end], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step(); dist.barrier()
+    te = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    dist.barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - te) / K], device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d = int(hx.numel() * 4 + hrp.numel() * hrp.element_size() + hcol.numel() * 4 + hew.numel() * 4)
+    e2e = {"value": E / float(e2e_s), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(r_loc * 4),
+           "ms_per_step": float(e2e_s) * 1e3, "api": "nerrf_b200.dist sharded step, per-rank pinned inputs (bytes are per rank)"}
+    tp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    traffic = json.load(open(tp)).get("sage_layer_F128_dram_bytes_per_launch") if os.path.exists(tp) else None
+    return {"metric": "graphsage_t_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph)",
+            "config": dict(workload_config(world), exchange=args.exchange),
+            "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
+                         "peak_source": peak_src, "per_layer_compute_ms": [float(v) for v in comp_ms],
+                         "per_layer_exchange_ms": [float(v) for v in comm_ms],
+                         "exchange_bytes_per_layer": int(N * HIDDEN * 4)},
+            "cpu_baseline": None,
+            "e2e": e2e,
+            "gpu_launches": K * LAYERS, "clocks": clocks, "mcts": mcts_local, "algo": args.algo}

@@ -1,0 +1,66 @@
+"""World-size-2 (and 3) gloo tests of the sharded GraphSAGE-T forward and root-parallel MCTS merge.
+The compute is the oracle (CPU); what is under test is the host-side sharding / exchange logic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nerrf_b200 import graph as G
+from nerrf_b200 import dist as ND
+from oracle import sage_ref as S
+from oracle import mcts_ref as M
+
+
+def _worker(rank, world, port, exchange, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = G.synthetic_graph(N=3000, E=30000, seed=5, hub="dst")          # skewed rows: uneven cuts
+        P = S.make_params(32, 128, 3, seed=1)
+        t = lambda a: torch.from_numpy(a)
+        shard = ND.Shard(g.rowptr, g.col, g.ew, rank, world)
+        full_col, full_ew = t(g.col), t(g.ew)
+        assert torch.equal(shard.col, full_col[shard.edge_base:shard.edge_end])
+
+        def layer_fn(l, h, out, sh):
+            W, b = P["layers"][l]
+            out[sh.row_begin:sh.row_end] = S.layer(h, t(g.rowptr), full_col, full_ew, W, b,
+                                                    row_begin=sh.row_begin, row_end=sh.row_end)
+
+        def head_fn(h, sh):
+            return torch.sigmoid(h[sh.row_begin:sh.row_end] @ P["node_w"] + P["node_b"])
+
+        h, score = ND.sharded_forward(layer_fn, 3, t(g.x), shard, 128, exchange=exchange, head_fn=head_fn)
+        hw, scw = S.forward(P, t(g.x), t(g.rowptr), full_col, full_ew)
+        ok = torch.allclose(h, hw, rtol=1e-5, atol=1e-6) and torch.allclose(score, scw[shard.row_begin:shard.row_end], atol=1e-6)
+        # root-parallel MCTS merge: every rank ends with the same merged statistics
+        rng = np.random.default_rng(0)
+        p = rng.beta(0.5, 0.5, 40).astype(np.float32); size = rng.lognormal(0.7, 1, 40).astype(np.float32)
+        cost = np.ones(40, np.float32)
+        fn = lambda off: (lambda r: (r["root_n"], r["root_w"]))(M.search(p, size, cost, R=64, D=10, T=6, seed=7 + off))
+        n, w = ND.root_parallel_search(fn, rank, world)
+        want_n = sum(M.search(p, size, cost, R=64, D=10, T=6, seed=7 + g_)["root_n"] for g_ in range(world))
+        ok = ok and np.array_equal(n, want_n)
+        q.put((rank, bool(ok), shard.row_begin, shard.row_end, w.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,exchange", [(2, "broadcast"), (2, "allreduce"), (3, "broadcast")])
+def test_sharded_forward_matches_single_process(world, exchange):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world * 7 + (3 if exchange == "allreduce" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    res.sort()
+    assert all(r[1] for r in res), res
+    assert res[0][2] == 0 and res[-1][3] == 3000 and all(a[3] == b[2] for a, b in zip(res, res[1:]))
+    assert len({r[4] for r in res}) == 1            # bit-identical merged MCTS value sums on every rank
