@@ -1,0 +1,33 @@
+"""torchrun --nproc-per-node N scripts/dist_check.py : sharded CUDA forward == single-GPU forward (bit-exact rows)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from nerrf_b200 import dist as ND, graph as G
+from nerrf_b200.ai.models import GraphSAGE_T
+from nerrf_b200.ai.planner import mcts
+from nerrf_b200.ai.planner.rewards import Actions
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+for exchange in ("broadcast", "allreduce"):
+    for hub in ("src", "dst"):
+        g = G.synthetic_graph(N=200_000, E=2_000_000, seed=3, hub=hub)
+        model = GraphSAGE_T(32, 128, 3).to(dev)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        x, rp, col, ew = t(g.x), t(g.rowptr), t(g.col), t(g.ew)
+        h_ref, sc_ref = model(x, rp, col, ew)
+        shard = ND.Shard(rp, col, ew, rank, world, device=dev)
+        layer = ND.cuda_layer_fn(model)
+        h, _ = ND.sharded_forward(lambda l, hin, out, sh: layer(l, hin, out, sh), 3, x, shard, 128, exchange=exchange)
+        ok = torch.equal(h, h_ref)
+        print(f"rank {rank} exchange={exchange} hub={hub}: rows [{shard.row_begin},{shard.row_end}) edges {shard.edge_end - shard.edge_base} "
+              f"full-matrix bit-exact={ok} max|diff|={float((h - h_ref).abs().max()):.2e}", flush=True)
+        assert ok or exchange == "allreduce" and float((h - h_ref).abs().max()) == 0.0
+# root-parallel MCTS
+rng = np.random.default_rng(2)
+act = Actions(rng.beta(0.5, 0.5, 256), rng.lognormal(0.7, 1.0, 256), np.ones(256))
+fn = lambda off: (lambda r: (r.root_n, r.root_w))(mcts.search(act, None, 1024, 30, 5 + off, iterations=16, device=dev))
+n, w = ND.root_parallel_search(fn, rank, world)
+print(f"rank {rank} merged root visits {int(n.sum())} best {mcts.best_child(n, w)}", flush=True)
+dist.barrier(); dist.destroy_process_group()
