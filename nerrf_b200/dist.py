@@ -5,8 +5,10 @@ GraphSAGE-T   1-D EDGE-BLOCK shards over the CSR-by-destination edge array with 
               therefore the contiguous edge block [rowptr[cuts[g]], rowptr[cuts[g+1]]).  Every rank
               keeps the full node-embedding matrix of the current layer; after each layer the ranks
               exchange the rows they produced (one collective per layer):
-                exchange="broadcast"  all-gather-v as one broadcast per owner (half the traffic of an
-                                      all-reduce, no fp32 re-association) -- default
+                exchange="allgather"  equal row blocks: ONE in-place all-gather per layer (half the traffic of
+                                      an all-reduce, no fp32 re-association); falls back to "broadcast" when
+                                      the blocks are uneven
+                exchange="broadcast"  all-gather-v as one broadcast per owner (edge-balanced uneven cuts)
                 exchange="allreduce"  the north star's contract: zero outside the owned rows, SUM
               The last layer's node scores stay sharded (each rank returns its rows).
 MCTS          root parallelism, no collective on the data path: rank g runs an independent tree with
@@ -31,9 +33,15 @@ from . import graph as G
 class Shard:
     """What one rank holds: full rowptr, its edge block of col / ew (indexed from edge_base)."""
 
-    def __init__(self, rowptr, col, ew, rank, world, device=None):
+    def __init__(self, rowptr, col, ew, rank, world, device=None, cut="edges"):
+        """cut="edges": edge-balanced row-aligned cuts (skewed graphs); cut="rows": equal row blocks (when the
+        in-degree is uniform these are edge-balanced too, and the exchange can be one in-place all-gather)."""
         rp = rowptr.cpu().numpy() if isinstance(rowptr, torch.Tensor) else np.asarray(rowptr)
-        self.cuts = G.edge_balanced_row_cuts(rp, world)
+        n = rp.shape[0] - 1
+        if cut == "rows":
+            self.cuts = np.array([(n * g) // world for g in range(world + 1)], dtype=np.int64)
+        else:
+            self.cuts = G.edge_balanced_row_cuts(rp, world)
         self.rank, self.world = rank, world
         self.row_begin, self.row_end = int(self.cuts[rank]), int(self.cuts[rank + 1])
         self.edge_base, self.edge_end = int(rp[self.row_begin]), int(rp[self.row_end])
@@ -53,6 +61,11 @@ def exchange_rows(buf, cuts, rank, world, mode="broadcast", group=None):
         rb, re = int(cuts[rank]), int(cuts[rank + 1])
         buf[:rb].zero_(); buf[re:].zero_()
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        return
+    sizes = np.diff(np.asarray(cuts))
+    if mode == "allgather" and (sizes == sizes[0]).all():
+        rb, re = int(cuts[rank]), int(cuts[rank + 1])
+        dist.all_gather_into_tensor(buf, buf[rb:re], group=group)       # in place: one collective per layer
         return
     works = []
     for g in range(world):
@@ -133,7 +146,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     from bench import N_NODES, N_EDGES, HIDDEN, LAYERS, F_IN
     N, E = N_NODES * world, N_EDGES * world
     rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev)
-    shard = Shard(rowptr, col, ew, rank, world, device=dev)
+    shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
     del col, ew
     torch.cuda.empty_cache()
     bufs = [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]

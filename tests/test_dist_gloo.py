@@ -21,7 +21,7 @@ def _worker(rank, world, port, exchange, q):
         g = G.synthetic_graph(N=3000, E=30000, seed=5, hub="dst")          # skewed rows: uneven cuts
         P = S.make_params(32, 128, 3, seed=1)
         t = lambda a: torch.from_numpy(a)
-        shard = ND.Shard(g.rowptr, g.col, g.ew, rank, world)
+        shard = ND.Shard(g.rowptr, g.col, g.ew, rank, world, cut="rows" if exchange == "allgather" else "edges")
         full_col, full_ew = t(g.col), t(g.ew)
         assert torch.equal(shard.col, full_col[shard.edge_base:shard.edge_end])
 
@@ -49,11 +49,11 @@ def _worker(rank, world, port, exchange, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,exchange", [(2, "broadcast"), (2, "allreduce"), (3, "broadcast")])
+@pytest.mark.parametrize("world,exchange", [(2, "broadcast"), (2, "allreduce"), (3, "broadcast"), (2, "allgather"), (3, "allgather")])
 def test_sharded_forward_matches_single_process(world, exchange):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world * 7 + (3 if exchange == "allreduce" else 0)
+    port = 29500 + (os.getpid() % 2000) + world * 7 + {"allreduce": 3, "broadcast": 0, "allgather": 5}[exchange]
     procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
