@@ -290,6 +290,7 @@ def run_ours(args):
         assert torch.equal(score_host, step().cpu()), "host-session scores differ from the device path"
 
         mcts_info = run_mcts_bench(dev, args)
+        lstm_info = run_lstm_bench(dev)
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import sage_ref as S
@@ -299,7 +300,7 @@ def run_ours(args):
         line = {"metric": "graphsage_t_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": gpu_launches, "clocks": clocks, "mcts": mcts_info, "algo": args.algo}
+                "gpu_launches": gpu_launches, "clocks": clocks, "mcts": mcts_info, "lstm": lstm_info, "algo": args.algo}
         print(json.dumps(line), flush=True)
         return
 
@@ -337,6 +338,22 @@ def run_mcts_bench(dev, args, seed=0):
     return {"metric": "mcts_rollouts_per_sec", "value": R * T / (ms * 1e-3), "unit": "rollouts/s", "ms_per_search": ms,
             "e2e_value": R * T / e2e_s, "config": {"actions": A, "rollouts_per_iteration": R, "depth": D, "iterations": T},
             "best_action": r.best, "note": "includes host-side setup/readback of the search call"}
+
+
+def run_lstm_bench(dev, B=4096, T=100):
+    """BiLSTM(256 x 2 layers) over B candidate-file sequences of T=100 events."""
+    import torch
+    from nerrf_b200.ai.models import lstm
+    model = lstm.LSTMScorer().to(dev)
+    seq = torch.randn(B, T, 16, device=dev)
+    lengths = torch.randint(T // 2, T + 1, (B,), device=dev)
+    model(seq, lengths); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); model(seq, lengths); model(seq, lengths); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    flops = B * T * 2.0 * (2 * 1024 * (16 + 256) + 2 * 1024 * (512 + 256))      # both directions, both layers
+    return {"metric": "lstm_sequences_per_sec", "value": B / (ms * 1e-3), "unit": "sequences/s", "ms": ms,
+            "tflops_fp32": flops / (ms * 1e-3) / 1e12, "config": {"batch": B, "T": T, "hidden": 256, "layers": 2}}
 
 
 def main():
