@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 namespace nerrf {
 
 constexpr int MAXD = 256;
-constexpr int MCTS_THREADS = 256;
+constexpr int MCTS_THREADS = 128;
 constexpr int MCTS_WARPS = MCTS_THREADS / 32;
 constexpr int MAXR = 8192;
 
@@ -84,9 +84,10 @@ __device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const float
 }
 
 // apply the j-th legal (zero) action, ascending a, to the warp-distributed state.  zl = this lane's
-// zero count, incl = inclusive prefix over lanes (both precomputed by the caller).
+// zero count, incl = inclusive prefix over lanes.  Both are UPDATED in place (the chosen lane loses one
+// zero, so every prefix from that lane on drops by one): no re-scan is needed for the next step.
 template <int NW>
-__device__ __forceinline__ void apply_jth(uint32_t (&w)[NW], int zl, int incl, int j, int lane) {
+__device__ __forceinline__ void apply_jth(uint32_t (&w)[NW], int& zl, int& incl, int j, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, incl > j);
     const int src = __ffs(m) - 1;
     if (lane == src) {
@@ -102,7 +103,9 @@ __device__ __forceinline__ void apply_jth(uint32_t (&w)[NW], int zl, int incl, i
                 rank -= pz;
             }
         }
+        zl -= 1;
     }
+    if (lane >= src) incl -= 1;
 }
 
 template <int NW>
@@ -157,10 +160,10 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     float* u_s = reinterpret_cast<float*>(smem_raw);
     float* v_s = u_s + A_PAD;
     float* c_s = v_s + A_PAD;
-    float* red = c_s + A_PAD;                 // [MAXR/2 + MAXR/4] tree-sum scratch (CTA 0)
     __shared__ uint32_t s_state[NWORDS];
     __shared__ int2 s_path[MAXD];
     __shared__ float s_key[MCTS_WARPS];
+    __shared__ float s_tree[MCTS_WARPS];
     __shared__ int s_arg[MCTS_WARPS];
     __shared__ int s_node, s_depth, s_plen, s_created, s_stop, s_L0, s_numnodes;
 
@@ -260,19 +263,19 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             for (int k = 0; k < NW; ++k) w[k] = s_state[lane * NW + k];
             int left = P.D - depth;
             int zl, incl, L;
+            lane_zero_scan<NW>(w, lane, zl, incl, L);                     // once; maintained incrementally below
             if (first_move) {
-                lane_zero_scan<NW>(w, lane, zl, incl, L);
                 apply_jth<NW>(w, zl, incl, r % L0, lane);
-                left -= 1;
+                L -= 1; left -= 1;
             }
             uint32_t rnd[4] = {0, 0, 0, 0};
             for (int k = 0; k < left; ++k) {
-                lane_zero_scan<NW>(w, lane, zl, incl, L);
                 if (L == 0) break;
                 if ((k & 3) == 0) philox4x32_10((uint32_t)r, (uint32_t)(k >> 2), (uint32_t)t, 0u, P.k0, P.k1, rnd);
                 const uint32_t xr = rnd[k & 3];
                 const int j = (int)__umulhi(xr, (uint32_t)L);
                 apply_jth<NW>(w, zl, incl, j, lane);
+                L -= 1;
             }
             const float sc = warp_score<NW>(w, u_s, v_s, c_s, lane);
             if (lane == 0) P.val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
@@ -293,25 +296,31 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             }
         }
         if (blockIdx.x == 0) {
-            // adjacent-pairs tree sum of val[0..R)
-            float* bufA = red;                 // R/2
-            float* bufB = red + MAXR / 2;      // R/4
-            int n = P.R;
-            float total;
-            if (n == 1) {
-                total = __ldcg(P.val);
-            } else {
-                for (int i = tid; i < n / 2; i += MCTS_THREADS) bufA[i] = __fadd_rn(__ldcg(P.val + 2 * i), __ldcg(P.val + 2 * i + 1));
-                n >>= 1;
-                __syncthreads();
-                float* src = bufA; float* dst = bufB;
-                while (n > 1) {
-                    for (int i = tid; i < n / 2; i += MCTS_THREADS) dst[i] = __fadd_rn(src[2 * i], src[2 * i + 1]);
-                    n >>= 1;
-                    __syncthreads();
-                    float* tmp = src; src = dst; dst = tmp;
-                }
-                total = src[0];
+            // adjacent-pairs tree sum of val[0..R): each thread reduces an aligned block of m values in
+            // registers / local memory, lanes combine with the xor butterfly (== adjacent pairs, lane i holds
+            // block i), warps with a fixed pairing.  Same tree as the oracle for any power-of-two R.
+            const int m = P.R >= MCTS_THREADS ? P.R / MCTS_THREADS : 1;
+            const int nthr = P.R / m;                                   // power of two <= MCTS_THREADS
+            float v = 0.f;
+            if (tid < nthr) {
+                float loc[MAXR / MCTS_THREADS];
+                for (int i = 0; i < m; ++i) loc[i] = __ldcg(P.val + tid * m + i);
+                for (int st = 1; st < m; st <<= 1)
+                    for (int i = 0; i < m; i += 2 * st) loc[i] = __fadd_rn(loc[i], loc[i + st]);
+                v = loc[0];
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float other = __shfl_xor_sync(0xffffffffu, v, o);
+                if (o < nthr) v = __fadd_rn(v, other);
+            }
+            if (lane == 0) s_tree[warp] = v;
+            __syncthreads();
+            float total = s_tree[0];
+            if (nthr > 32) {
+                float a01 = __fadd_rn(s_tree[0], s_tree[1]);
+                total = a01;
+                if (nthr > 64) total = __fadd_rn(a01, __fadd_rn(s_tree[2], s_tree[3]));
             }
             const int plen = s_plen;
             for (int i = tid; i < plen; i += MCTS_THREADS) {
@@ -386,7 +395,7 @@ static MctsLayout mcts_layout(int A, int T, int R) {
 
 template <int NW>
 static int launch_mcts(MctsArgs& args, cudaStream_t st) {
-    const size_t smem = (size_t)3 * 1024 * NW * 4 + (size_t)(MAXR / 2 + MAXR / 4) * 4;
+    const size_t smem = (size_t)3 * 1024 * NW * 4;
     NERRF_CHECK_CUDA(cudaFuncSetAttribute(mcts_search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NERRF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcts_search_kernel<NW>, MCTS_THREADS, smem));
