@@ -12,10 +12,11 @@
 //            legal action = warp prefix-sum of popcounts + __fns; reward = per-lane sequential
 //            sum over its 32*NW actions (terms staged in smem, transposed -> conflict-free)
 //            + xor-butterfly; value written to val[r]
-//   grid.sync
+//   grid barrier (monotonic counter: one atomicAdd + ld.acquire spin per CTA; co-residency is guaranteed by
+//                 the cooperative launch; cheaper than cg::grid.sync with one fat CTA per SM)
 //   backup   CTA 0: adjacent-pairs tree sum of val -> path edges; all CTAs: per-first-action
 //            child statistics of the leaf (fixed ascending-r order)
-//   grid.sync
+//   grid barrier
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -24,7 +25,7 @@ namespace cg = cooperative_groups;
 namespace nerrf {
 
 constexpr int MAXD = 256;
-constexpr int MCTS_THREADS = 128;
+constexpr int MCTS_THREADS = 896;     // 28 warps: one CTA per SM covers 4096 rollouts in a single pass (148 x 28)
 constexpr int MCTS_WARPS = MCTS_THREADS / 32;
 constexpr int MAXR = 8192;
 
@@ -133,6 +134,21 @@ __device__ __forceinline__ int kth_zero_serial(const uint32_t* s, int n_words, i
     return -1;
 }
 
+// Grid-wide barrier on a monotonically increasing counter (zeroed by the host before the launch).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();                                   // publish this CTA's writes
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
 struct MctsArgs {
     const float *p, *size, *cost;
     int A;
@@ -150,12 +166,13 @@ struct MctsArgs {
     int32_t* child_id;
     float* val;          // [R]
     int32_t* g_num_nodes;
+    unsigned* barrier;   // grid barrier counter (zero at launch)
 };
 
 template <int NW>
 __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     constexpr int CHUNK = 32 * NW, A_PAD = 1024 * NW, NWORDS = 32 * NW;
-    cg::grid_group grid = cg::this_grid();
+    unsigned bar_target = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* u_s = reinterpret_cast<float*>(smem_raw);
     float* v_s = u_s + A_PAD;
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             const float sc = warp_score<NW>(w, u_s, v_s, c_s, lane);
             if (lane == 0) P.val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
         }
-        grid.sync();
+        grid_barrier(P.barrier, bar_target);
 
         // ------------------------------------------------------------------ backup
         if (first_move) {   // leaf children: rank q -> action, fixed ascending-r accumulation
@@ -299,11 +316,12 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             // adjacent-pairs tree sum of val[0..R): each thread reduces an aligned block of m values in
             // registers / local memory, lanes combine with the xor butterfly (== adjacent pairs, lane i holds
             // block i), warps with a fixed pairing.  Same tree as the oracle for any power-of-two R.
-            const int m = P.R >= MCTS_THREADS ? P.R / MCTS_THREADS : 1;
-            const int nthr = P.R / m;                                   // power of two <= MCTS_THREADS
+            constexpr int TS = 512;                                     // threads used by the tree sum (power of two)
+            const int m = P.R >= TS ? P.R / TS : 1;
+            const int nthr = P.R / m;                                   // power of two <= TS
             float v = 0.f;
             if (tid < nthr) {
-                float loc[MAXR / MCTS_THREADS];
+                float loc[MAXR / TS];
                 for (int i = 0; i < m; ++i) loc[i] = __ldcg(P.val + tid * m + i);
                 for (int st = 1; st < m; st <<= 1)
                     for (int i = 0; i < m; i += 2 * st) loc[i] = __fadd_rn(loc[i], loc[i + st]);
@@ -317,10 +335,17 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             if (lane == 0) s_tree[warp] = v;
             __syncthreads();
             float total = s_tree[0];
-            if (nthr > 32) {
-                float a01 = __fadd_rn(s_tree[0], s_tree[1]);
-                total = a01;
-                if (nthr > 64) total = __fadd_rn(a01, __fadd_rn(s_tree[2], s_tree[3]));
+            if (nthr > 32) {                                            // second level: warp sums, same adjacent pairing
+                const int nw = nthr / 32;                               // 2, 4, 8 or 16
+                float u = (warp == 0 && lane < nw) ? s_tree[lane] : 0.f;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const float other = __shfl_xor_sync(0xffffffffu, u, o);
+                    if (o < nw) u = __fadd_rn(u, other);
+                }
+                if (tid == 0) s_tree[0] = u;
+                __syncthreads();
+                total = s_tree[0];
             }
             const int plen = s_plen;
             for (int i = tid; i < plen; i += MCTS_THREADS) {
@@ -339,7 +364,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                 }
             }
         }
-        grid.sync();
+        grid_barrier(P.barrier, bar_target);
     }
     // ---------------------------------------------------------------------- outputs
     if (blockIdx.x == 0) {
@@ -376,7 +401,7 @@ __global__ void __launch_bounds__(256) reward_score_kernel(const uint32_t* __res
 static int nw_for(int A) { return A <= 1024 ? 1 : (A <= 2048 ? 2 : 4); }
 
 struct MctsLayout {
-    size_t visits, child_n, child_w, child_id, val, numnodes, total;
+    size_t visits, child_n, child_w, child_id, val, numnodes, barrier, total;
 };
 static MctsLayout mcts_layout(int A, int T, int R) {
     const size_t A_pad = 1024 * (size_t)nw_for(A);
@@ -387,6 +412,7 @@ static MctsLayout mcts_layout(int A, int T, int R) {
     L.child_n = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
     L.child_w = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
     L.numnodes = o; o = al(o + 4);
+    L.barrier = o; o = al(o + 4);
     L.child_id = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
     L.val = o; o = al(o + (size_t)R * 4);
     L.total = o;
@@ -474,7 +500,7 @@ extern "C" int nerrf_mcts_search(const float* p, const float* size, const float*
     a.c = c; a.lo = lo; a.inv_range = inv_range; a.lnN = ln_table;
     a.root_n = root_n; a.root_w = root_w; a.num_nodes_out = num_nodes;
     a.visits = (int32_t*)(ws + L.visits); a.child_n = (int32_t*)(ws + L.child_n); a.child_w = (float*)(ws + L.child_w);
-    a.child_id = (int32_t*)(ws + L.child_id); a.val = (float*)(ws + L.val); a.g_num_nodes = (int32_t*)(ws + L.numnodes);
+    a.child_id = (int32_t*)(ws + L.child_id); a.val = (float*)(ws + L.val); a.g_num_nodes = (int32_t*)(ws + L.numnodes); a.barrier = (unsigned*)(ws + L.barrier);
     const int NW = nw_for(A);
     if (NW == 1) return launch_mcts<1>(a, st);
     if (NW == 2) return launch_mcts<2>(a, st);
