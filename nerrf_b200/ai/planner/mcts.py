@@ -66,12 +66,68 @@ def merge_root_stats(results):
     return n, w, best_child(n, w)
 
 
+class SearchContext:
+    """Device-resident state for repeated searches over the same candidate set (plan() re-roots up to
+    `depth` times): the action arrays, ln table, tree workspace and pinned result buffers are allocated
+    once; a search is then memset + one persistent kernel + one small D2H."""
+
+    def __init__(self, actions: Actions, n_rollouts=4096, depth=50, iterations=64, c=math.sqrt(2.0), device=None):
+        self.actions, self.R, self.D, self.T, self.c = actions, int(n_rollouts), int(depth), int(iterations), float(c)
+        if self.R < 1 or (self.R & (self.R - 1)):
+            raise ValueError("n_rollouts must be a power of two")
+        self.device = torch.device(device or "cuda")
+        if self.device.type != "cuda":
+            raise L.NerrfError("mcts.search needs a CUDA device (no CPU fallback)")
+        A = actions.A
+        _, _, self.A_pad, self.nw = RW.layout(A)
+        with torch.cuda.device(self.device):
+            self.p, self.size, self.cost = actions.device_arrays(self.device)
+            self.d_ln = torch.from_numpy(ln_table(self.T, self.R)).to(self.device)
+            self.d_root = torch.empty(self.nw, device=self.device, dtype=torch.int32)
+            # root_n | root_w | num_nodes in one buffer -> one D2H
+            self.d_out = torch.empty(2 * self.A_pad + 1, device=self.device, dtype=torch.int32)
+            self.h_out = torch.empty(2 * self.A_pad + 1, dtype=torch.int32).pin_memory()
+            self.h_root = torch.empty(self.nw, dtype=torch.int32).pin_memory()
+            need = C.c_size_t()
+            L.check(L.lib().nerrf_mcts_workspace_bytes(A, self.T, self.R, C.byref(need)), "nerrf_mcts_workspace_bytes")
+            self.ws_bytes = need.value
+            self.ws = torch.empty(need.value, device=self.device, dtype=torch.uint8)
+
+    def launch(self, seed=0, root_state=None, depth=None):
+        """Enqueue one search on the current stream (asynchronous); returns (lo, inv_range)."""
+        A = self.actions.A
+        root = RW.empty_state(A) if root_state is None else (np.asarray(root_state, np.uint32) | RW.empty_state(A))
+        lo, inv = RW.reward_bounds(self.actions, root)
+        self.h_root.copy_(torch.from_numpy(root.view(np.int32)))
+        self.d_root.copy_(self.h_root, non_blocking=True)
+        o = self.d_out
+        L.check(L.lib().nerrf_mcts_search(L.ptr(self.p), L.ptr(self.size), L.ptr(self.cost), A, L.ptr(self.d_root), self.R,
+                                          self.D if depth is None else int(depth), self.T, C.c_uint64(seed), self.c,
+                                          float(lo), float(inv), L.ptr(self.d_ln), C.c_void_p(o.data_ptr()),
+                                          C.c_void_p(o.data_ptr() + 4 * self.A_pad), C.c_void_p(o.data_ptr() + 8 * self.A_pad),
+                                          L.ptr(self.ws), self.ws_bytes, L.current_stream_ptr()), "nerrf_mcts_search")
+        return float(lo), float(inv)
+
+    def fetch(self, lo, inv) -> "SearchResult":
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        A, Ap = self.actions.A, self.A_pad
+        h = self.h_out.numpy()
+        root_n = h[:A].copy(); root_w = h[Ap:Ap + A].view(np.float32).copy(); nn = int(h[2 * Ap])
+        return SearchResult(root_n, root_w, best_child(root_n, root_w), nn, lo, inv, self.R * self.T)
+
+    def search(self, seed=0, root_state=None, depth=None) -> "SearchResult":
+        with torch.cuda.device(self.device):
+            lo, inv = self.launch(seed, root_state, depth)
+            return self.fetch(lo, inv)
+
+
 def search(actions: Actions, scorer=None, n_rollouts: int = 4096, depth: int = 50, seed: int = 0,
-           c: float = math.sqrt(2.0), iterations: int = 64, root_state=None, device=None, host_call: bool = False
-           ) -> SearchResult:
+           c: float = math.sqrt(2.0), iterations: int = 64, root_state=None, device=None, host_call: bool = False,
+           context: SearchContext | None = None) -> SearchResult:
     """One tree search.  `scorer` must be None or ai.planner.rewards.score: the reward is evaluated
     inside the kernel (batched, R states per iteration).  host_call=True goes through the
-    host-buffer C-ABI entry (copies inside the call)."""
+    host-buffer C-ABI entry (copies inside the call).  Pass a SearchContext to reuse device buffers."""
     if scorer is not None and scorer is not RW.score:
         raise NotImplementedError("the CUDA planner evaluates ai.planner.rewards.score in-kernel; "
                                   "custom scorers are not supported")
@@ -80,36 +136,19 @@ def search(actions: Actions, scorer=None, n_rollouts: int = 4096, depth: int = 5
     R, D, T = int(n_rollouts), int(depth), int(iterations)
     if R < 1 or (R & (R - 1)):
         raise ValueError("n_rollouts must be a power of two")
-    root = RW.empty_state(A) if root_state is None else (np.asarray(root_state, np.uint32) | RW.empty_state(A))
-    lo, inv = RW.reward_bounds(actions, root)
-    lnN = ln_table(T, R)
-    lib = L.lib()
     if host_call:
+        root = RW.empty_state(A) if root_state is None else (np.asarray(root_state, np.uint32) | RW.empty_state(A))
+        lo, inv = RW.reward_bounds(actions, root)
+        lnN = ln_table(T, R)
         root_n = np.zeros(A_pad, np.int32); root_w = np.zeros(A_pad, np.float32); nn = np.zeros(1, np.int32)
         as_p = lambda a: a.ctypes.data_as(C.c_void_p)
-        L.check(lib.nerrf_mcts_search_host(as_p(actions.p), as_p(actions.size), as_p(actions.cost), A, as_p(root), R, D, T,
-                                           C.c_uint64(seed), float(c), float(lo), float(inv), as_p(lnN), as_p(root_n),
-                                           as_p(root_w), as_p(nn)), "nerrf_mcts_search_host")
+        L.check(L.lib().nerrf_mcts_search_host(as_p(actions.p), as_p(actions.size), as_p(actions.cost), A, as_p(root), R, D, T,
+                                               C.c_uint64(seed), float(c), float(lo), float(inv), as_p(lnN), as_p(root_n),
+                                               as_p(root_w), as_p(nn)), "nerrf_mcts_search_host")
         return SearchResult(root_n[:A].copy(), root_w[:A].copy(), best_child(root_n[:A], root_w[:A]), int(nn[0]),
                             float(lo), float(inv), R * T)
-    device = torch.device(device or "cuda")
-    if device.type != "cuda":
-        raise L.NerrfError("mcts.search needs a CUDA device (no CPU fallback)")
-    with torch.cuda.device(device):
-        p, size, cost = actions.device_arrays(device)
-        d_root = torch.from_numpy(root.view(np.int32)).to(device)
-        d_ln = torch.from_numpy(lnN).to(device)
-        d_n = torch.empty(A_pad, device=device, dtype=torch.int32)
-        d_w = torch.empty(A_pad, device=device, dtype=torch.float32)
-        d_nn = torch.empty(1, device=device, dtype=torch.int32)
-        need = C.c_size_t()
-        L.check(lib.nerrf_mcts_workspace_bytes(A, T, R, C.byref(need)), "nerrf_mcts_workspace_bytes")
-        ws = torch.empty(need.value, device=device, dtype=torch.uint8)
-        L.check(lib.nerrf_mcts_search(L.ptr(p), L.ptr(size), L.ptr(cost), A, L.ptr(d_root), R, D, T, C.c_uint64(seed),
-                                      float(c), float(lo), float(inv), L.ptr(d_ln), L.ptr(d_n), L.ptr(d_w), L.ptr(d_nn),
-                                      L.ptr(ws), need.value, L.current_stream_ptr()), "nerrf_mcts_search")
-        root_n = d_n.cpu().numpy()[:A].copy(); root_w = d_w.cpu().numpy()[:A].copy(); nn = int(d_nn.cpu())
-    return SearchResult(root_n, root_w, best_child(root_n, root_w), nn, float(lo), float(inv), R * T)
+    ctx = context or SearchContext(actions, R, D, T, c, device)
+    return ctx.search(seed, root_state, depth=D)
 
 
 @dataclass
@@ -140,8 +179,9 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
     max_steps = depth if max_steps is None else max_steps
     cur = float(RW.score(state[None, :], actions, device=device).cpu()[0])
     out = Plan([], [cur], [])
+    ctx = SearchContext(actions, n_rollouts, depth, iterations, c, device)
     for step in range(max_steps):
-        res = search(actions, None, n_rollouts, max(depth - step, 1), seed + step, c, iterations, state, device)
+        res = ctx.search(seed + step, state, depth=max(depth - step, 1))
         out.searches.append(res)
         cand = ranked_children(res.root_n, res.root_w)
         if cand.size == 0:
