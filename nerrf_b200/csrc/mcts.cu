@@ -85,25 +85,31 @@ __device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const float
 }
 
 // apply the j-th legal (zero) action, ascending a, to the warp-distributed state.  zl = this lane's
-// zero count, incl = inclusive prefix over lanes.  Both are UPDATED in place (the chosen lane loses one
-// zero, so every prefix from that lane on drops by one): no re-scan is needed for the next step.
+// zero count, incl = inclusive prefix over lanes; both are UPDATED in place (the chosen lane loses one
+// zero, so every prefix from that lane on drops by one): no re-scan for the next step.
+// The n-th-set-bit search inside the chosen word is done by the whole warp: the word is broadcast,
+// lane b tests "bit b is legal and exactly `rank` legal bits lie below it", one ballot finds b.
 template <int NW>
 __device__ __forceinline__ void apply_jth(uint32_t (&w)[NW], int& zl, int& incl, int j, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, incl > j);
     const int src = __ffs(m) - 1;
-    if (lane == src) {
-        int rank = j - (incl - zl);
+    int rank = j - (incl - zl);                       // meaningful in lane `src` only
+    int kk = 0;
+    uint32_t zsel = ~w[0];
 #pragma unroll
-        for (int k = 0; k < NW; ++k) {
-            const uint32_t z = ~w[k];
-            const int pz = __popc(z);
-            if (rank >= 0 && rank < pz) {
-                w[k] |= 1u << __fns(z, 0, rank + 1);
-                rank = -1;
-            } else if (rank >= 0) {
-                rank -= pz;
-            }
-        }
+    for (int k = 1; k < NW; ++k) {                    // pick the word that holds the rank-th legal bit of this lane
+        const int pz = __popc(zsel);
+        const bool next = (kk == k - 1) && (rank >= pz);
+        if (next) { rank -= pz; kk = k; zsel = ~w[k]; }
+    }
+    const uint32_t z = __shfl_sync(0xffffffffu, zsel, src);
+    const int rk = __shfl_sync(0xffffffffu, rank, src);
+    const bool hit = ((z >> lane) & 1u) && (__popc(z & ((1u << lane) - 1u)) == rk);
+    const int bit = __ffs(__ballot_sync(0xffffffffu, hit)) - 1;
+    if (lane == src) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            if (k == kk) w[k] |= 1u << bit;
         zl -= 1;
     }
     if (lane >= src) incl -= 1;
@@ -144,6 +150,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v < target) __nanosleep(32);
         } while (v < target);
     }
     __syncthreads();
@@ -285,14 +292,17 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                 apply_jth<NW>(w, zl, incl, r % L0, lane);
                 L -= 1; left -= 1;
             }
-            uint32_t rnd[4] = {0, 0, 0, 0};
-            for (int k = 0; k < left; ++k) {
-                if (L == 0) break;
-                if ((k & 3) == 0) philox4x32_10((uint32_t)r, (uint32_t)(k >> 2), (uint32_t)t, 0u, P.k0, P.k1, rnd);
-                const uint32_t xr = rnd[k & 3];
-                const int j = (int)__umulhi(xr, (uint32_t)L);
-                apply_jth<NW>(w, zl, incl, j, lane);
-                L -= 1;
+            for (int k = 0; k < left && L > 0; k += 4) {                  // one Philox call feeds four steps
+                uint32_t rnd[4];
+                philox4x32_10((uint32_t)r, (uint32_t)(k >> 2), (uint32_t)t, 0u, P.k0, P.k1, rnd);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (k + q < left && L > 0) {
+                        const int j = (int)__umulhi(rnd[q], (uint32_t)L);
+                        apply_jth<NW>(w, zl, incl, j, lane);
+                        L -= 1;
+                    }
+                }
             }
             const float sc = warp_score<NW>(w, u_s, v_s, c_s, lane);
             if (lane == 0) P.val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
