@@ -75,6 +75,17 @@ int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is6
                               int relu, int algo, const float* node_w, float node_b, float* score,
                               nerrf_stream_t stream);
 
+/* Full-option layer call.  node_w == NULL: no fused head.  long_ws (optional device scratch, size from
+ * nerrf_sage_long_rows_workspace_bytes): destination rows with more than 512 in-edges ("hub" rows) are
+ * pre-aggregated chunk-wise by many CTAs into it instead of being gathered by a single warp; rows that do
+ * not fit in the scratch (or long_ws == NULL) are processed inline -- same result, slower. */
+int nerrf_sage_long_rows_workspace_bytes(int64_t n_edges, size_t* bytes);
+int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                            const float* ew, const float* W, const float* b, float* out,
+                            int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
+                            int relu, int algo, const float* node_w, float node_b, float* score,
+                            void* long_ws, size_t long_ws_bytes, nerrf_stream_t stream);
+
 /* Heads.  score[v] = sigmoid(h_v . node_w + node_b).  If edge_W != NULL also writes
  * proj[v] = (h_v.We[0:H,0], h_v.We[0:H,1], h_v.We[H:2H,0], h_v.We[H:2H,1])  (proj [n,4]). */
 int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,
@@ -87,7 +98,8 @@ int nerrf_sage_edge_head(const float* proj, const void* rowptr, int rowptr_is64,
 
 /* Whole forward on device pointers: L layers + node head.  W[l] is [2F_l, H], b[l] is [H]
  * (host arrays of device pointers).  h_out [n_nodes,H]; score_out [n_nodes]; workspace must
- * hold n_nodes*H floats when L > 1. */
+ * hold n_nodes*H floats when L > 1; any bytes beyond that (256-aligned) are used as the hub-row scratch
+ * (see nerrf_sage_long_rows_workspace_bytes). */
 int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
                        const float* ew, int64_t n_nodes, int f_in, int hidden, int num_layers,
                        const float* const* W, const float* const* b, const float* node_w,

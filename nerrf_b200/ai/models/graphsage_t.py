@@ -110,14 +110,24 @@ class GraphSAGE_T(nn.Module):
             colp = C.c_void_p(col.data_ptr() - 4 * edge_base); ewp = C.c_void_p(edge_w.data_ptr() - 4 * edge_base)
         else:
             colp, ewp = L.ptr(col), L.ptr(edge_w)
-        args = (L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b),
-                L.ptr(out), N, row_begin, row_end, h.shape[1], self.hidden, int(relu), ALGOS[self.algo])
-        if score_out is None:
-            L.check(L.lib().nerrf_sage_layer_fwd(*args, L.current_stream_ptr()), "nerrf_sage_layer_fwd")
-        else:
-            L.check(L.lib().nerrf_sage_layer_head_fwd(*args, L.ptr(self.node_w), self._node_b_host(), L.ptr(score_out),
-                                                      L.current_stream_ptr()), "nerrf_sage_layer_head_fwd")
+        lws, lws_bytes = self._long_rows_ws(col.numel(), h.device)
+        L.check(L.lib().nerrf_sage_layer_fwd_ex(
+            L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
+            row_begin, row_end, h.shape[1], self.hidden, int(relu), ALGOS[self.algo],
+            L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
+            L.ptr(score_out), L.ptr(lws), lws_bytes, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
         return out
+
+    def _long_rows_ws(self, n_edges, device):
+        """Device scratch for the hub-row pre-aggregation (include/nerrf_b200.h); cached, grows with E."""
+        import ctypes as C
+        need = C.c_size_t()
+        L.check(L.lib().nerrf_sage_long_rows_workspace_bytes(int(n_edges), C.byref(need)), "long_rows_workspace_bytes")
+        ws = getattr(self, "_lws", None)
+        if ws is None or ws.numel() < need.value or ws.device != device:
+            ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+            self._lws = ws
+        return ws, need.value
 
     def heads(self, h, rowptr, col, return_edge_logits=False, row_begin=0, row_end=None):
         N = h.shape[0]
@@ -148,12 +158,14 @@ class GraphSAGE_T(nn.Module):
         dev = x.device
         h = torch.empty(N, self.hidden, device=dev, dtype=torch.float32)
         score = torch.empty(N, device=dev, dtype=torch.float32)
-        ws = torch.empty(N, self.hidden, device=dev, dtype=torch.float32) if self.num_layers > 1 else None
+        _, lbytes = self._long_rows_ws(col.numel(), dev)
+        pp = ((N * self.hidden * 4 + 255) // 256) * 256 if self.num_layers > 1 else 0
+        ws = torch.empty(pp + lbytes, device=dev, dtype=torch.uint8)
         Wp = L.ptr_array(list(self.weights)); bp = L.ptr_array(list(self.biases))
         L.check(L.lib().nerrf_sage_forward(L.ptr(x), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col),
                                            L.ptr(edge_w), N, self.in_dim, self.hidden, self.num_layers, Wp, bp,
                                            L.ptr(self.node_w), self._node_b_host(), L.ptr(h), L.ptr(score), L.ptr(ws),
-                                           0 if ws is None else ws.numel() * 4, ALGOS[self.algo],
+                                           ws.numel(), ALGOS[self.algo],
                                            L.current_stream_ptr()), "nerrf_sage_forward")
         if return_edge_logits and self.edge_W is not None:
             _, el = self.heads(h, rowptr, col, return_edge_logits=True)

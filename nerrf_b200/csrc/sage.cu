@@ -13,7 +13,7 @@ namespace nerrf {
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew,
                     const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin,
                     int64_t row_end, int F, int relu, int nsplit, const float* node_w, float node_b, float* score,
-                    cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
+                    void* long_ws, size_t long_ws_bytes, cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
 bool sage_umma_available();
 
 // ------------------------------------------------------------------------------------------
@@ -280,7 +280,7 @@ extern "C" int nerrf_sage_aggregate(const float* x, const void* rowptr, int rowp
 static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col, const float* ew,
                           const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end,
                           int F, int H, int relu, int algo, const float* node_w, float node_b, float* score,
-                          nerrf_stream_t stream) {
+                          void* long_ws, size_t long_ws_bytes, nerrf_stream_t stream) {
     int rc = check_graph_args(x, rowptr, col, ew, n_nodes, row_begin, row_end);
     if (rc) return rc;
     NERRF_REQUIRE(W && b && out, "null weight/output pointer");
@@ -293,7 +293,7 @@ static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, c
     if (algo == NERRF_SAGE_ALGO_AUTO) algo = sage_umma_available() ? NERRF_SAGE_ALGO_UMMA : NERRF_SAGE_ALGO_FFMA;
     if (algo == NERRF_SAGE_ALGO_UMMA || algo == NERRF_SAGE_ALGO_UMMA2)
         return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu,
-                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, st);
+                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, long_ws, long_ws_bytes, st);
     NERRF_REQUIRE(algo == NERRF_SAGE_ALGO_FFMA, "unknown algo %d", algo);
     rc = rowptr_is64
              ? layer_dispatch<int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st)
@@ -307,7 +307,7 @@ extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowp
                                     int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
                                     nerrf_stream_t stream) {
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo,
-                          nullptr, 0.f, nullptr, stream);
+                          nullptr, 0.f, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
@@ -316,7 +316,24 @@ extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int
                                          const float* node_w, float node_b, float* score, nerrf_stream_t stream) {
     NERRF_REQUIRE(node_w && score, "null head pointer");
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
-                          node_b, score, stream);
+                          node_b, score, nullptr, 0, stream);
+}
+
+extern "C" int nerrf_sage_long_rows_workspace_bytes(int64_t n_edges, size_t* bytes) {
+    NERRF_REQUIRE(bytes && n_edges >= 0, "bad argument");
+    // every 512-edge chunk of a hub row + one spare chunk per hub row (<= n_edges/512 of them); 560 B per chunk item
+    const int64_t items = 2 * (n_edges / 512) + 64;
+    *bytes = (size_t)items * 560 + 8192;
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
+                                       const float* ew, const float* W, const float* b, float* out, int64_t n_nodes,
+                                       int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
+                                       const float* node_w, float node_b, float* score, void* long_ws,
+                                       size_t long_ws_bytes, nerrf_stream_t stream) {
+    return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
+                          node_b, score, long_ws, long_ws_bytes, stream);
 }
 
 extern "C" int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,
@@ -364,6 +381,10 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
         }
     }
     if (score_out) NERRF_REQUIRE(node_w, "node_w required for score_out");
+    // workspace beyond the [n_nodes, hidden] ping-pong buffer (if any) is the hub-row pre-aggregation scratch
+    const size_t pp = num_layers > 1 ? (((size_t)n_nodes * hidden * sizeof(float) + 255) & ~(size_t)255) : 0;
+    void* long_ws = (workspace && workspace_bytes > pp + 8192) ? (void*)((unsigned char*)workspace + pp) : nullptr;
+    const size_t long_ws_bytes = long_ws ? workspace_bytes - pp : 0;
     const float* in = x;
     int F = f_in;
     for (int l = 0; l < num_layers; ++l) {
@@ -371,7 +392,7 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
         const bool last = l == num_layers - 1;
         int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1, algo,
                                 (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
-                                stream);
+                                long_ws, long_ws_bytes, stream);
         if (rc) return rc;
         in = o;
         F = hidden;
@@ -380,6 +401,12 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
 }
 
 // ------------------------------------------------------------------------------------------ session
+static size_t session_ws_bytes(int64_t max_nodes, int64_t max_edges, int hidden) {
+    size_t lb = 0;
+    nerrf_sage_long_rows_workspace_bytes(max_edges, &lb);
+    return (((size_t)max_nodes * hidden * 4 + 255) & ~(size_t)255) + lb;
+}
+
 struct nerrf_sage_session {
     int64_t max_nodes, max_edges;
     int f_in, hidden, L;
@@ -407,7 +434,7 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
     A((void**)&s->col, (size_t)max_edges * 4);
     A((void**)&s->ew, (size_t)max_edges * 4);
     A((void**)&s->h, (size_t)max_nodes * hidden * 4);
-    A((void**)&s->ws, (size_t)max_nodes * hidden * 4);
+    A((void**)&s->ws, session_ws_bytes(max_nodes, max_edges, hidden));
     A((void**)&s->score, (size_t)max_nodes * 4);
     A((void**)&s->node_w, (size_t)hidden * 4);
     int F = f_in;
@@ -456,7 +483,7 @@ extern "C" int nerrf_sage_session_forward_host(nerrf_sage_session* s, const floa
     NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
     NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
     int rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
-                                s->node_w, s->node_b, s->h, s->score, s->ws, (size_t)s->max_nodes * s->hidden * 4, algo, st);
+                                s->node_w, s->node_b, s->h, s->score, s->ws, session_ws_bytes(s->max_nodes, s->max_edges, s->hidden), algo, st);
     if (rc) return rc;
     if (score_out_host)
         NERRF_CHECK_CUDA(cudaMemcpyAsync(score_out_host, s->score, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, st));

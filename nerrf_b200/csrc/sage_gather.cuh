@@ -16,10 +16,11 @@ namespace nerrf {
 //
 // 2*UH load instructions (2*UH*G source rows) are issued BEFORE anything is consumed.  Weights are
 // re-broadcast at consume time instead of being held in registers.
+// wsum_out != nullptr: return the UNNORMALISED weighted sum and store the weight sum (used for chunk partials).
 template <int F, bool PRE = false, int UH = 0>
 __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const int32_t* __restrict__ col,
                                               const float* __restrict__ ew, int64_t e0, int64_t e1, int lane,
-                                              int pre_c = 0, float pre_w = 0.f) {
+                                              int pre_c = 0, float pre_w = 0.f, float* wsum_out = nullptr) {
     constexpr int LPR = F / 4;        // lanes per source row
     constexpr int G = 32 / LPR;       // source rows per load instruction
     constexpr int U = UH > 0 ? UH : ((G == 1) ? 4 : 2);   // load instructions per half batch

@@ -235,12 +235,125 @@ __device__ __forceinline__ uint32_t b_offset(int r, int k) {
     return (uint32_t)(kb * (TN * 128) + r * 128 + (((chunk ^ (r & 7)) << 4) | ((col & 7) << 1)));
 }
 
+// ---------------------------------------------------------------- long rows (hub destinations)
+// A destination row with more than LONG_T in-edges would be gathered by ONE warp.  A deterministic pre-pass
+// cuts every such row into fixed chunks of LONG_CH edges; one CTA per chunk computes the unnormalised
+// weighted sum + weight sum (fixed order: 8 warps x 64 edges, then warp 0 adds the 8 warp partials in order)
+// into a side buffer.  The main kernel then sees the row as the items [self, partial_0 .. partial_{nc-1}]
+// (weight 1 each, weight-sum from pw[]).  The workspace is capacity driven: rows that do not fit stay inline.
+constexpr int LONG_T = 512;            // == EMAX: such a row can never be fully staged anyway
+constexpr int LONG_CH = 512;
+
+struct LongWs {
+    int* hdr;              // [0] = number of chunk items claimed (may exceed cap), [1] = cap
+    int* hash_key;         // row + 1, 0 = empty
+    int* hash_val;         // first item of the row
+    int2* queue;           // (row - row_begin? no: absolute row as two ints) -> see pack/unpack
+    float* partial;        // [cap][128]
+    float* pw;             // [cap]
+    int cap;
+    int hash_mask;         // slots - 1 (slots = power of two >= 2 * cap)
+};
+
+__host__ __device__ inline size_t long_ws_bytes_for(int cap, int slots) {
+    return 256 + (size_t)slots * 8 + (size_t)cap * (8 + 128 * 4 + 4);
+}
+static LongWs long_ws_carve(void* ws, size_t bytes) {
+    LongWs L{};
+    if (!ws || bytes < 8192) return L;
+    int cap = (int)((bytes - 256) / (8 + 128 * 4 + 4 + 32));        // 32 B/item covers the hash (>= 2 slots x 8 B, rounded up)
+    if (cap < 4) return L;
+    int slots = 1;
+    while (slots < 2 * cap) slots <<= 1;
+    while (long_ws_bytes_for(cap, slots) > bytes && cap > 4) { cap = cap * 3 / 4; slots = 1; while (slots < 2 * cap) slots <<= 1; }
+    if (long_ws_bytes_for(cap, slots) > bytes) return L;
+    unsigned char* b = (unsigned char*)ws;
+    L.hdr = (int*)b; b += 256;
+    L.hash_key = (int*)b; b += (size_t)slots * 4;
+    L.hash_val = (int*)b; b += (size_t)slots * 4;
+    L.queue = (int2*)b; b += (size_t)cap * 8;
+    L.partial = (float*)b; b += (size_t)cap * 128 * 4;
+    L.pw = (float*)b;
+    L.cap = cap; L.hash_mask = slots - 1;
+    return L;
+}
+__device__ __forceinline__ int long_hash(int64_t row, int mask) { return (int)(((uint64_t)row * 0x9E3779B97F4A7C15ull) >> 40) & mask; }
+__device__ __forceinline__ int long_lookup(const LongWs& L, int64_t row) {      // first item of `row`, or -1
+    int h = long_hash(row, L.hash_mask);
+    const int key = (int)row + 1;
+    for (int probe = 0; probe <= L.hash_mask; ++probe) {
+        const int k = L.hash_key[h];
+        if (k == key) return L.hash_val[h];
+        if (k == 0) return -1;
+        h = (h + 1) & L.hash_mask;
+    }
+    return -1;
+}
+
+template <typename RP>
+__global__ void __launch_bounds__(256) long_scan_kernel(const RP* __restrict__ rowptr, int64_t row_begin, int64_t row_end, LongWs L) {
+    for (int64_t row = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t deg = (int64_t)rowptr[row + 1] - (int64_t)rowptr[row];
+        if (deg <= LONG_T) continue;
+        const int nch = (int)((deg + LONG_CH - 1) / LONG_CH);
+        const int first = atomicAdd(L.hdr, nch);
+        if (first + nch > L.cap) continue;                               // does not fit: the row stays inline
+        for (int c = 0; c < nch; ++c) L.queue[first + c] = make_int2((int)row, c);
+        int h = long_hash(row, L.hash_mask);
+        const int key = (int)row + 1;
+        while (atomicCAS(L.hash_key + h, 0, key) != 0) h = (h + 1) & L.hash_mask;
+        L.hash_val[h] = first;
+    }
+}
+
+template <int F, typename RP>
+__global__ void __launch_bounds__(256) long_chunk_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr,
+                                                         const int32_t* __restrict__ col, const float* __restrict__ ew, LongWs L) {
+    __shared__ float4 s_acc[8][32];
+    __shared__ float s_w[8];
+    constexpr int LPR = F / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n_items = L.hdr[0];
+    if (n_items > L.cap) n_items = L.cap;                                // items past cap were never queued ...
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+        const int2 it = L.queue[i];
+        if (it.x < 0) continue;                                          // claimed by a row that did not fit (never queued)
+        const int64_t e0 = (int64_t)rowptr[it.x], e1 = (int64_t)rowptr[it.x + 1];
+        const int64_t c0 = e0 + (int64_t)it.y * LONG_CH;
+        const int64_t c1 = (c0 + LONG_CH < e1) ? c0 + LONG_CH : e1;
+        const int64_t a = c0 + warp * (LONG_CH / 8);
+        int64_t b = a + LONG_CH / 8;
+        if (b > c1) b = c1;
+        float wsum = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a < b) acc = gather_row<F>(x, col, ew, a, b, lane, 0, 0.f, &wsum);
+        if (lane < LPR) s_acc[warp][lane] = acc;
+        if (lane == 0) s_w[warp] = wsum;
+        __syncthreads();
+        if (warp == 0) {
+            if (lane < LPR) {
+                float4 t = s_acc[0][lane];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) { t.x += s_acc[k][lane].x; t.y += s_acc[k][lane].y; t.z += s_acc[k][lane].z; t.w += s_acc[k][lane].w; }
+                *reinterpret_cast<float4*>(L.partial + (size_t)i * 128 + 4 * lane) = t;
+            }
+            if (lane == 0) {
+                float t = s_w[0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) t += s_w[k];
+                L.pw[i] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int F, int NS, typename RP>
 __global__ void __launch_bounds__((UmmaCfg<F, NS>::THREADS), 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
                        float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu,
-                       const float* __restrict__ node_w, float node_b, float* __restrict__ score) {
+                       const float* __restrict__ node_w, float node_b, float* __restrict__ score, const LongWs lw) {
     using C = UmmaCfg<F, NS>;
     constexpr int K = C::K, LPR = F / 4;
     constexpr int GATHER_WARPS = C::GATHER_WARPS, IDX_STAGES = C::IDX_STAGES;
@@ -326,9 +439,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         const int stream_end = tiles_mine * TN;
 
         // ---- per-row state, issue side (i*) and consume side (c*)
-        int ii = g, ib = 0, inb = 1, ie0 = 0, ideg = -1, itl = -1;  uint32_t irow = 0;
+        int ii = g, ib = 0, inb = 1, ie0 = 0, ideg = -1, itl = -1, ilong = -1, iitems = 0;  uint32_t irow = 0;
         const int32_t* icol = nullptr; int64_t ielo = 0;
-        int ci = g, cb = 0, cnb = 1, ce0 = 0, cdeg = -1, ctl = -1;
+        int ci = g, cb = 0, cnb = 1, ce0 = 0, cdeg = -1, ctl = -1, clong = -1, citems = 0;
         const float* cew = nullptr; int64_t celo = 0;
 
         auto setup_issue_row = [&]() {                                  // ii < stream_end
@@ -348,7 +461,13 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 irow = (uint32_t)row;
                 ie0 = rp_s[r];
                 ideg = rp_s[r + 1] - ie0;
-                inb = (ideg + QS) / QS;                                  // ceil((deg + 1) / QS)
+                iitems = ideg + 1;                                       // [self, edges...]
+                ilong = -1;
+                if (ideg > LONG_T && lw.cap > 0) {                       // hub row: [self, chunk partials...] if pre-aggregated
+                    ilong = long_lookup(lw, row);
+                    if (ilong >= 0) iitems = 1 + (ideg + LONG_CH - 1) / LONG_CH;
+                }
+                inb = (iitems + QS - 1) / QS;
             }
         };
         auto setup_consume_row = [&]() {                                // ci < stream_end, tile already staged
@@ -363,7 +482,13 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             if (row < row_end) {
                 ce0 = rp_s[r];
                 cdeg = rp_s[r + 1] - ce0;
-                cnb = (cdeg + QS) / QS;
+                citems = cdeg + 1;
+                clong = -1;
+                if (cdeg > LONG_T && lw.cap > 0) {
+                    clong = long_lookup(lw, row);
+                    if (clong >= 0) citems = 1 + (cdeg + LONG_CH - 1) / LONG_CH;
+                }
+                cnb = (citems + QS - 1) / QS;
             }
         };
         // one cp.async group = sub-batch `ib` of the issue row, into ring slot `slot`
@@ -371,7 +496,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             if (ii < stream_end) {
                 if (ideg >= 0) {
                     const int first = ib * QS;
-                    const int nitems = ideg + 1 - first;                 // items left in the row (>= 1)
+                    const int nitems = iitems - first;                   // items left in the row (>= 1)
                     const uint32_t dst = ring_u32 + (uint32_t)(slot * SLOT_FLOATS * 4);
                     const int kbase = ie0 + first - 1;                   // item `it` of this sub-batch is edge kbase + it
                     if (ie0 + ideg <= EMAX) {                            // whole row staged (the common case): branch free
@@ -382,6 +507,16 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 #pragma unroll
                         for (int t = 0; t < QS; t += G)
                             cp_async16_pred(dst + (uint32_t)(t * F * 4), xs + (size_t)src[t / G] * F, t + grp < nitems);
+                    } else if (ilong >= 0) {                             // hub row: items are pre-aggregated chunk partials
+#pragma unroll
+                        for (int t = 0; t < QS; t += G) {
+                            const int it = t + grp;
+                            if (it < nitems) {
+                                const float* srcp = (first + it == 0) ? xs + (size_t)irow * F
+                                                                      : lw.partial + (size_t)(ilong + first + it - 1) * 128 + 4 * sub;
+                                cp_async16(dst + (uint32_t)(t * F * 4), srcp);
+                            }
+                        }
                     } else {
 #pragma unroll
                         for (int t = 0; t < QS; t += G) {
@@ -419,7 +554,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             islot = (islot + 1) % NQ;
             if (cdeg >= 0) {
                 const int first = cb * QS;
-                const int nitems = cdeg + 1 - first;
+                const int nitems = citems - first;
                 const float* rs = ring_gen + cslot * SLOT_FLOATS;
                 const int kbase = ce0 + first - 1;
                 if (ce0 + cdeg <= EMAX) {                                // whole row staged: batched LDS, predicated math
@@ -449,6 +584,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                             const float4 v = *reinterpret_cast<const float4*>(rs + t * F);
                             if (t == 0 && first + it == 0) {
                                 self = v;
+                            } else if (clong >= 0) {                     // chunk partial: already weighted
+                                wsum += lw.pw[clong + first + it - 1];
+                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                             } else {
                                 const int k = kbase + it;
                                 const float w = (k < EMAX) ? cew[k] : __ldg(ew + celo + k);
@@ -639,7 +777,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
-                cudaStream_t st) {
+                void* long_ws, size_t long_ws_bytes, cudaStream_t st) {
     using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -649,8 +787,20 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     const int64_t rows = row_end - row_begin;
     const int64_t tiles = (rows + TN - 1) / TN;
     if (tiles == 0) return NERRF_OK;
+    LongWs lw = long_ws_carve(long_ws, long_ws_bytes);
+    if (lw.cap > 0) {
+        // hub-row pre-pass: clear header + hash, mark the queue empty, find long rows, aggregate their chunks
+        const size_t hash_bytes = (size_t)(lw.hash_mask + 1) * 8;
+        NERRF_CHECK_CUDA(cudaMemsetAsync(lw.hdr, 0, 256 + hash_bytes, st));
+        NERRF_CHECK_CUDA(cudaMemsetAsync(lw.queue, 0xFF, (size_t)lw.cap * 8, st));
+        const int sms = sm_count();
+        long_scan_kernel<RP><<<sms * 4, 256, 0, st>>>(rowptr, row_begin, row_end, lw);
+        long_chunk_kernel<F, RP><<<sms * 4, 256, 0, st>>>(x, rowptr, col, ew, lw);
+        int rc = launch_status("long-row pre-pass");
+        if (rc) return rc;
+    }
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score);
+    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
     return launch_status("sage_layer_umma_kernel");
 }
 
@@ -660,11 +810,12 @@ bool sage_umma_available() { return true; }
 
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
-                    int nsplit, const float* node_w, float node_b, float* score, cudaStream_t st) {
+                    int nsplit, const float* node_w, float node_b, float* score, void* long_ws, size_t long_ws_bytes,
+                    cudaStream_t st) {
     (void)n_nodes;
-#define GO(FV, NSV)                                                                                                                                   \
-    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, st) \
-                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, st)
+#define GO(FV, NSV)                                                                                                                                                            \
+    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, st) \
+                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, st)
     if (nsplit == 3) {
         switch (F) {
             case 32: GO(32, 3);

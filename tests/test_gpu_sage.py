@@ -177,3 +177,27 @@ def test_fused_head_matches_separate_head(algo):
     score2 = torch.full((7001,), -1.0, device="cuda")
     model.layer_forward(0, x, rp, col, ew, row_begin=100, row_end=6000, score_out=score2)
     assert torch.equal(score2[100:6000], score[100:6000]) and (score2[:100] == -1).all() and (score2[6000:] == -1).all()
+
+
+@pytest.mark.parametrize("F", [32, 128])
+def test_hub_rows_preaggregated_path_matches_inline_and_oracle(F):
+    """Rows with > 512 in-edges take the chunk pre-aggregation path; same answer as the inline path and the oracle."""
+    rng = np.random.default_rng(F)
+    N, E = 4000, 120000
+    dst = np.minimum((N * rng.random(E) ** 6).astype(np.int64), N - 1)          # a few rows with 10^3..10^4 in-edges
+    src = rng.integers(0, N, E)
+    t = (rng.random(E) * 60).astype(np.float32); conf = (0.5 + 0.5 * rng.random(E)).astype(np.float32)
+    rowptr, col, ew = G.csr_from_edges(src, dst, t, conf, N)
+    assert np.diff(rowptr).max() > 5000
+    g = G.TemporalGraph(rowptr, col, ew, rng.standard_normal((N, F)).astype(np.float32), {})
+    model = GraphSAGE_T(F, 128, 1, algo="umma").cuda()
+    x, rp, c, w = dev_graph(g)
+    out = model.layer_forward(0, x, rp, c, w)                                    # with the hub-row scratch
+    W, b = model.oracle_params()["layers"][0]
+    assert_close_fp32(out, S.layer(*cpu_graph(g), W, b), what="hub rows vs oracle")
+    # inline path (no scratch) through the plain C-ABI entry
+    out2 = torch.empty_like(out)
+    L.check(L.lib().nerrf_sage_layer_fwd(L.ptr(x), L.ptr(rp), 0, L.ptr(c), L.ptr(w), L.ptr(model.weights[0]),
+                                         L.ptr(model.biases[0]), L.ptr(out2), N, 0, N, F, 128, 1, 2, L.current_stream_ptr()))
+    assert_close_fp32(out2, out, what="inline vs pre-aggregated")
+    assert torch.equal(out, model.layer_forward(0, x, rp, c, w))                 # deterministic
