@@ -67,6 +67,7 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const 
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
     const float wsum = warp_sum(wpart);
+    if (wsum_out) { *wsum_out = wsum; return acc; }          // unnormalised partial (hub-row chunks)
     const float inv = 1.0f / fmaxf(wsum, 1e-12f);
     acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     return acc;
