@@ -262,10 +262,11 @@ static LongWs long_ws_carve(void* ws, size_t bytes) {
     LongWs L{};
     if (!ws || bytes < 8192) return L;
     int cap = (int)((bytes - 256) / (8 + 128 * 4 + 4 + 32));        // 32 B/item covers the hash (>= 2 slots x 8 B, rounded up)
+    cap &= ~3;                                                       // keeps every sub-array 16-byte aligned
     if (cap < 4) return L;
     int slots = 1;
     while (slots < 2 * cap) slots <<= 1;
-    while (long_ws_bytes_for(cap, slots) > bytes && cap > 4) { cap = cap * 3 / 4; slots = 1; while (slots < 2 * cap) slots <<= 1; }
+    while (long_ws_bytes_for(cap, slots) > bytes && cap > 4) { cap = (cap * 3 / 4) & ~3; slots = 1; while (slots < 2 * cap) slots <<= 1; }
     if (long_ws_bytes_for(cap, slots) > bytes) return L;
     unsigned char* b = (unsigned char*)ws;
     L.hdr = (int*)b; b += 256;
