@@ -233,7 +233,8 @@ def run_ours(args):
             for l in range(LAYERS):
                 out = bufs[l & 1]
                 # the node head is fused into the last layer's epilogue
-                model.layer_forward(l, inp, rp, col, ew, out=out, score_out=score if l == LAYERS - 1 else None)
+                model.layer_forward(l, inp, rp, col, ew, out=out, score_out=score if l == LAYERS - 1 else None,
+                                    reuse_long_scan=l > 0)
                 if i is not None: ev[i][l + 1].record()
                 inp = out
             return score

@@ -42,6 +42,10 @@ extern "C" {
                                     (6 MMAs per K step; fp32-equivalent accuracy)           */
 #define NERRF_SAGE_ALGO_UMMA2 3  /* same with a 2-term split (3 MMAs; ~1e-5 relative)       */
 
+/* OR into `algo` of nerrf_sage_layer_fwd_ex: long_ws already holds the hub-row scan of THIS graph and row
+ * range (it depends on rowptr only), e.g. layers 2..L of one forward: skip the re-scan. */
+#define NERRF_SAGE_FLAG_REUSE_LONG_SCAN 0x100
+
 typedef void* nerrf_stream_t;    /* cudaStream_t */
 
 int nerrf_abi_version(void);

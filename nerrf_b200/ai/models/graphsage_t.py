@@ -95,10 +95,12 @@ class GraphSAGE_T(nn.Module):
 
     # -- single layer (used by the sharded forward) ---------------------------------------
     def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None,
-                      edge_base: int = 0):
+                      edge_base: int = 0, reuse_long_scan: bool = False):
         """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue.
         edge_base: `col` / `edge_w` hold only the edge block [edge_base, edge_base + len) of the graph (a
-        1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data."""
+        1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data.
+        reuse_long_scan: the previous layer_forward call on this model used the SAME graph and row range, so
+        the hub-row scan held in the scratch is still valid (layers 2..L of one forward)."""
         self._check_graph(h, rowptr, col, edge_w)
         N = h.shape[0]
         row_end = N if row_end is None else row_end
@@ -111,9 +113,10 @@ class GraphSAGE_T(nn.Module):
         else:
             colp, ewp = L.ptr(col), L.ptr(edge_w)
         lws, lws_bytes = self._long_rows_ws(col.numel(), h.device)
+        algo_flags = ALGOS[self.algo] | (0x100 if reuse_long_scan else 0)
         L.check(L.lib().nerrf_sage_layer_fwd_ex(
             L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
-            row_begin, row_end, h.shape[1], self.hidden, int(relu), ALGOS[self.algo],
+            row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
             L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
             L.ptr(score_out), L.ptr(lws), lws_bytes, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
         return out

@@ -13,7 +13,7 @@ namespace nerrf {
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew,
                     const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin,
                     int64_t row_end, int F, int relu, int nsplit, const float* node_w, float node_b, float* score,
-                    void* long_ws, size_t long_ws_bytes, cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
+                    void* long_ws, size_t long_ws_bytes, bool reuse_scan, cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
 bool sage_umma_available();
 
 // ------------------------------------------------------------------------------------------
@@ -290,10 +290,13 @@ static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, c
     NERRF_REQUIRE(x != out, "in-place layer is not supported");
     NERRF_REQUIRE(!node_w || score, "score output required with node_w");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool reuse_scan = (algo & NERRF_SAGE_FLAG_REUSE_LONG_SCAN) != 0;
+    algo &= 0xFF;
     if (algo == NERRF_SAGE_ALGO_AUTO) algo = sage_umma_available() ? NERRF_SAGE_ALGO_UMMA : NERRF_SAGE_ALGO_FFMA;
     if (algo == NERRF_SAGE_ALGO_UMMA || algo == NERRF_SAGE_ALGO_UMMA2)
         return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu,
-                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, long_ws, long_ws_bytes, st);
+                               algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, long_ws, long_ws_bytes,
+                               reuse_scan, st);
     NERRF_REQUIRE(algo == NERRF_SAGE_ALGO_FFMA, "unknown algo %d", algo);
     rc = rowptr_is64
              ? layer_dispatch<int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, F, relu, st)
@@ -390,7 +393,8 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
     for (int l = 0; l < num_layers; ++l) {
         float* o = ((num_layers - 1 - l) % 2 == 0) ? h_out : workspace;
         const bool last = l == num_layers - 1;
-        int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1, algo,
+        int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1,
+                                (algo & 0xFF) | (l > 0 ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0),
                                 (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
                                 long_ws, long_ws_bytes, stream);
         if (rc) return rc;

@@ -778,7 +778,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
-                void* long_ws, size_t long_ws_bytes, cudaStream_t st) {
+                void* long_ws, size_t long_ws_bytes, bool reuse_scan, cudaStream_t st) {
     using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -791,11 +791,13 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     LongWs lw = long_ws_carve(long_ws, long_ws_bytes);
     if (lw.cap > 0) {
         // hub-row pre-pass: clear header + hash, mark the queue empty, find long rows, aggregate their chunks
-        const size_t hash_bytes = (size_t)(lw.hash_mask + 1) * 8;
-        NERRF_CHECK_CUDA(cudaMemsetAsync(lw.hdr, 0, 256 + hash_bytes, st));
-        NERRF_CHECK_CUDA(cudaMemsetAsync(lw.queue, 0xFF, (size_t)lw.cap * 8, st));
         const int sms = sm_count();
-        long_scan_kernel<RP><<<sms * 4, 256, 0, st>>>(rowptr, row_begin, row_end, lw);
+        if (!reuse_scan) {       // the scan (hub-row list, hash, chunk queue) depends on the graph only, not on x
+            const size_t hash_bytes = (size_t)(lw.hash_mask + 1) * 8;
+            NERRF_CHECK_CUDA(cudaMemsetAsync(lw.hdr, 0, 256 + hash_bytes, st));
+            NERRF_CHECK_CUDA(cudaMemsetAsync(lw.queue, 0xFF, (size_t)lw.cap * 8, st));
+            long_scan_kernel<RP><<<sms * 4, 256, 0, st>>>(rowptr, row_begin, row_end, lw);
+        }
         long_chunk_kernel<F, RP><<<sms * 4, 256, 0, st>>>(x, rowptr, col, ew, lw);
         int rc = launch_status("long-row pre-pass");
         if (rc) return rc;
@@ -812,11 +814,11 @@ bool sage_umma_available() { return true; }
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
                     int nsplit, const float* node_w, float node_b, float* score, void* long_ws, size_t long_ws_bytes,
-                    cudaStream_t st) {
+                    bool reuse_scan, cudaStream_t st) {
     (void)n_nodes;
-#define GO(FV, NSV)                                                                                                                                                            \
-    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, st) \
-                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, st)
+#define GO(FV, NSV)                                                                                                                                                                        \
+    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, st) \
+                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, st)
     if (nsplit == 3) {
         switch (F) {
             case 32: GO(32, 3);

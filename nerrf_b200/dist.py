@@ -136,7 +136,8 @@ def cuda_layer_fn(model):
     """layer_fn for sharded_forward backed by the CUDA kernels (edge block addressed via edge_base)."""
     def fn(l, h, out, shard, score_out=None):
         model.layer_forward(l, h, shard.rowptr, shard.col, shard.ew, out=out, row_begin=shard.row_begin,
-                            row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out)
+                            row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out,
+                            reuse_long_scan=l > 0)
     return fn
 
 
