@@ -112,7 +112,7 @@ class GraphSAGE_T(nn.Module):
             colp = C.c_void_p(col.data_ptr() - 4 * edge_base); ewp = C.c_void_p(edge_w.data_ptr() - 4 * edge_base)
         else:
             colp, ewp = L.ptr(col), L.ptr(edge_w)
-        lws, lws_bytes = self._long_rows_ws(col.numel(), h.device)
+        lws, lws_bytes = self._long_rows_ws(col.numel(), h.device) if self._has_hub_rows(rowptr) else (None, 0)
         algo_flags = ALGOS[self.algo] | (0x100 if reuse_long_scan else 0)
         L.check(L.lib().nerrf_sage_layer_fwd_ex(
             L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
@@ -120,6 +120,16 @@ class GraphSAGE_T(nn.Module):
             L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
             L.ptr(score_out), L.ptr(lws), lws_bytes, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
         return out
+
+    def _has_hub_rows(self, rowptr) -> bool:
+        """Graph metadata (max in-degree > 512?), computed once per rowptr tensor (one device sync) and cached.
+        A stale cache entry can only cost speed, never correctness: without the scratch hub rows are
+        processed inline, with it the pre-pass simply finds nothing."""
+        key = (rowptr.data_ptr(), rowptr.numel(), rowptr._version)
+        if getattr(self, "_hub_key", None) != key:
+            self._hub_key = key
+            self._hub_val = bool((rowptr[1:] - rowptr[:-1]).max() > 512) if rowptr.numel() > 1 else False
+        return self._hub_val
 
     def _long_rows_ws(self, n_edges, device):
         """Device scratch for the hub-row pre-aggregation (include/nerrf_b200.h); cached, grows with E."""
@@ -161,7 +171,7 @@ class GraphSAGE_T(nn.Module):
         dev = x.device
         h = torch.empty(N, self.hidden, device=dev, dtype=torch.float32)
         score = torch.empty(N, device=dev, dtype=torch.float32)
-        _, lbytes = self._long_rows_ws(col.numel(), dev)
+        lbytes = self._long_rows_ws(col.numel(), dev)[1] if self._has_hub_rows(rowptr) else 0
         pp = ((N * self.hidden * 4 + 255) // 256) * 256 if self.num_layers > 1 else 0
         ws = torch.empty(pp + lbytes, device=dev, dtype=torch.uint8)
         Wp = L.ptr_array(list(self.weights)); bp = L.ptr_array(list(self.biases))
