@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(256) long_chunk_kernel(const float* __restrict
     }
 }
 
-template <int F, int NS, typename RP>
+// LONG: compiled with the hub-row (pre-aggregated partial items) paths; the plain variant is used when the
+// launch has no hub-row scratch, so graphs without hub rows pay nothing for the feature.
+template <int F, int NS, typename RP, bool LONG>
 __global__ void __launch_bounds__((UmmaCfg<F, NS>::THREADS), 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
@@ -464,7 +466,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 ideg = rp_s[r + 1] - ie0;
                 iitems = ideg + 1;                                       // [self, edges...]
                 ilong = -1;
-                if (ideg > LONG_T && lw.cap > 0) {                       // hub row: [self, chunk partials...] if pre-aggregated
+                if (LONG && ideg > LONG_T && lw.cap > 0) {               // hub row: [self, chunk partials...] if pre-aggregated
                     ilong = long_lookup(lw, row);
                     if (ilong >= 0) iitems = 1 + (ideg + LONG_CH - 1) / LONG_CH;
                 }
@@ -485,7 +487,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 cdeg = rp_s[r + 1] - ce0;
                 citems = cdeg + 1;
                 clong = -1;
-                if (cdeg > LONG_T && lw.cap > 0) {
+                if (LONG && cdeg > LONG_T && lw.cap > 0) {
                     clong = long_lookup(lw, row);
                     if (clong >= 0) citems = 1 + (cdeg + LONG_CH - 1) / LONG_CH;
                 }
@@ -508,7 +510,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 #pragma unroll
                         for (int t = 0; t < QS; t += G)
                             cp_async16_pred(dst + (uint32_t)(t * F * 4), xs + (size_t)src[t / G] * F, t + grp < nitems);
-                    } else if (ilong >= 0) {                             // hub row: items are pre-aggregated chunk partials
+                    } else if (LONG && ilong >= 0) {                     // hub row: items are pre-aggregated chunk partials
 #pragma unroll
                         for (int t = 0; t < QS; t += G) {
                             const int it = t + grp;
@@ -585,7 +587,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                             const float4 v = *reinterpret_cast<const float4*>(rs + t * F);
                             if (t == 0 && first + it == 0) {
                                 self = v;
-                            } else if (clong >= 0) {                     // chunk partial: already weighted
+                            } else if (LONG && clong >= 0) {             // chunk partial: already weighted
                                 wsum += lw.pw[clong + first + it - 1];
                                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                             } else {
@@ -782,7 +784,8 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
-        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_set = true;
     }
     const int64_t rows = row_end - row_begin;
@@ -803,7 +806,10 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
         if (rc) return rc;
     }
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    sage_layer_umma_kernel<F, NS, RP><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
+    if (lw.cap > 0)
+        sage_layer_umma_kernel<F, NS, RP, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
+    else
+        sage_layer_umma_kernel<F, NS, RP, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
     return launch_status("sage_layer_umma_kernel");
 }
 
