@@ -7,6 +7,7 @@
 // registers, h lives in shared memory).  Weights are pre-transposed ([K, 4H]) so the 256
 // threads read 1 KB contiguous per (k, gate); they stream from L2 every step (8.2 MB of
 // weights is L2-resident, too big for one SM's shared memory).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace nerrf {
@@ -181,7 +182,9 @@ extern "C" int nerrf_lstm_forward(const float* seq, const int32_t* len, int64_t 
     float* hfin = buf1 + (size_t)B * T * 2 * H;
     const float* in = seq;
     int sb = T * D_in, stt = D_in, D = D_in;
-    const bool big = B >= (int64_t)sm_count() * 4;
+    // NERRF_LSTM_BS=8|16 overrides the batch-tile heuristic (tuning aid)
+    const char* bs_env = getenv("NERRF_LSTM_BS");
+    const bool big = bs_env ? atoi(bs_env) == 16 : B >= (int64_t)sm_count() * 4;
     for (int l = 0; l < num_layers; ++l) {
         float* o = (l == num_layers - 1) ? nullptr : ((l & 1) ? buf1 : buf0);
         if (big)
