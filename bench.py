@@ -374,9 +374,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "umma", "umma2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "broadcast", "allreduce"],
-                    help="N>1: per-layer embedding exchange (in-place all-gather of equal row blocks, all-gather-v "
-                         "by broadcasts, or the all-reduce contract)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather", "broadcast", "allreduce"],
+                    help="N>1: per-layer embedding exchange: p2p = fused into the layer kernel (epilogue stores to "
+                         "peer-mapped buffers over NVLink); allgather / broadcast / allreduce = NCCL collectives")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

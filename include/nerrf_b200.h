@@ -88,7 +88,12 @@ int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int rowptr_is64,
                             const float* ew, const float* W, const float* b, float* out,
                             int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
                             int relu, int algo, const float* node_w, float node_b, float* score,
-                            void* long_ws, size_t long_ws_bytes, nerrf_stream_t stream);
+                            void* long_ws, size_t long_ws_bytes, float* const* peer_out, int n_peers,
+                            nerrf_stream_t stream);
+/* peer_out (host array of n_peers <= 7 device pointers, or NULL): peer-mapped [n_nodes, H] buffers of the other
+ * ranks of a 1-D sharded forward (CUDA IPC / symmetric memory over NVLink).  The layer's epilogue stores each
+ * output row to `out` AND to every peer buffer: the per-layer embedding exchange is fused into the layer
+ * kernel.  The caller provides the cross-rank barrier between layers. */
 
 /* Heads.  score[v] = sigmoid(h_v . node_w + node_b).  If edge_W != NULL also writes
  * proj[v] = (h_v.We[0:H,0], h_v.We[0:H,1], h_v.We[H:2H,0], h_v.We[H:2H,1])  (proj [n,4]). */

@@ -95,12 +95,14 @@ class GraphSAGE_T(nn.Module):
 
     # -- single layer (used by the sharded forward) ---------------------------------------
     def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None,
-                      edge_base: int = 0, reuse_long_scan: bool = False):
+                      edge_base: int = 0, reuse_long_scan: bool = False, peer_outs=None):
         """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue.
         edge_base: `col` / `edge_w` hold only the edge block [edge_base, edge_base + len) of the graph (a
         1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data.
         reuse_long_scan: the previous layer_forward call on this model used the SAME graph and row range, so
-        the hub-row scan held in the scratch is still valid (layers 2..L of one forward)."""
+        the hub-row scan held in the scratch is still valid (layers 2..L of one forward).
+        peer_outs: list of peer-mapped [N, H] tensors (other ranks' `out` buffers): the epilogue also stores
+        the produced rows there (fused per-layer exchange of the sharded forward, nerrf_b200.dist)."""
         self._check_graph(h, rowptr, col, edge_w)
         N = h.shape[0]
         row_end = N if row_end is None else row_end
@@ -118,7 +120,8 @@ class GraphSAGE_T(nn.Module):
             L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
             row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
             L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
-            L.ptr(score_out), L.ptr(lws), lws_bytes, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
+            L.ptr(score_out), L.ptr(lws), lws_bytes, L.ptr_array(peer_outs) if peer_outs else None,
+            len(peer_outs) if peer_outs else 0, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
         return out
 
     def _has_hub_rows(self, rowptr) -> bool:

@@ -235,6 +235,16 @@ __device__ __forceinline__ uint32_t b_offset(int r, int k) {
     return (uint32_t)(kb * (TN * 128) + r * 128 + (((chunk ^ (r & 7)) << 4) | ((col & 7) << 1)));
 }
 
+// ---------------------------------------------------------------- fused exchange (multi-GPU)
+// Peer-mapped [n_nodes, 128] embedding buffers of the other ranks (NVLink P2P, CUDA IPC / symmetric memory).
+// The epilogue stores every output row slice to the local buffer AND to each peer buffer, so the per-layer
+// embedding exchange of the 1-D sharded forward happens inside the layer kernel, overlapped tile by tile.
+constexpr int MAX_PEERS = 7;
+struct Peers {
+    float* out[MAX_PEERS];
+    int n;
+};
+
 // ---------------------------------------------------------------- long rows (hub destinations)
 // A destination row with more than LONG_T in-edges would be gathered by ONE warp.  A deterministic pre-pass
 // cuts every such row into fixed chunks of LONG_CH edges; one CTA per chunk computes the unnormalised
@@ -356,7 +366,8 @@ __global__ void __launch_bounds__((UmmaCfg<F, NS>::THREADS), 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
                        float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu,
-                       const float* __restrict__ node_w, float node_b, float* __restrict__ score, const LongWs lw) {
+                       const float* __restrict__ node_w, float node_b, float* __restrict__ score, const LongWs lw,
+                       const Peers peers) {
     using C = UmmaCfg<F, NS>;
     constexpr int K = C::K, LPR = F / 4;
     constexpr int GATHER_WARPS = C::GATHER_WARPS, IDX_STAGES = C::IDX_STAGES;
@@ -752,7 +763,13 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             for (int j = 0; j < 32; ++j) {
                 float o = __uint_as_float(v[j]) + my_bias;
                 if (relu) o = fmaxf(o, 0.f);
-                if (row0 + j < row_end) out[(row0 + j) * UM + f] = o;
+                if (row0 + j < row_end) {
+                    const int64_t off = (row0 + j) * UM + f;
+                    out[off] = o;
+#pragma unroll
+                    for (int pr = 0; pr < MAX_PEERS; ++pr)                              // fused exchange: NVLink P2P stores
+                        if (pr < peers.n) peers.out[pr][off] = o;
+                }
                 hv[j] = o * my_nw;
             }
             if (node_w) {
@@ -780,7 +797,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
-                void* long_ws, size_t long_ws_bytes, bool reuse_scan, cudaStream_t st) {
+                void* long_ws, size_t long_ws_bytes, bool reuse_scan, const Peers& peers, cudaStream_t st) {
     using C = UmmaCfg<F, NS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -807,9 +824,9 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     }
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
     if (lw.cap > 0)
-        sage_layer_umma_kernel<F, NS, RP, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
+        sage_layer_umma_kernel<F, NS, RP, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
     else
-        sage_layer_umma_kernel<F, NS, RP, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw);
+        sage_layer_umma_kernel<F, NS, RP, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
     return launch_status("sage_layer_umma_kernel");
 }
 
@@ -820,11 +837,15 @@ bool sage_umma_available() { return true; }
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
                     int nsplit, const float* node_w, float node_b, float* score, void* long_ws, size_t long_ws_bytes,
-                    bool reuse_scan, cudaStream_t st) {
+                    bool reuse_scan, float* const* peer_out, int n_peers, cudaStream_t st) {
     (void)n_nodes;
-#define GO(FV, NSV)                                                                                                                                                                        \
-    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, st) \
-                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, st)
+    Peers peers{};
+    if (n_peers < 0 || n_peers > MAX_PEERS) { set_error("n_peers must be in 0..%d", MAX_PEERS); return NERRF_ERR_INVALID; }
+    for (int i = 0; i < n_peers; ++i) peers.out[i] = peer_out[i];
+    peers.n = n_peers;
+#define GO(FV, NSV)                                                                                                                                                                               \
+    return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, peers, st) \
+                : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, peers, st)
     if (nsplit == 3) {
         switch (F) {
             case 32: GO(32, 3);

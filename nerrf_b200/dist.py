@@ -53,6 +53,42 @@ class Shard:
         self.num_nodes = self.rowptr.numel() - 1
 
 
+class PeerBuffers:
+    """Two [N, hidden] embedding buffers per rank, each mapped into every other rank's address space over
+    NVLink (torch symmetric memory; CUDA-IPC fallback).  With these the layer kernel's epilogue writes its rows
+    straight into the peers' buffers (exchange="p2p": the fused compute + collective form) and the only
+    per-layer collective left is a tiny cross-rank barrier."""
+
+    def __init__(self, N, hidden, device, rank, world, group=None):
+        self.rank, self.world = rank, world
+        self.hdls = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = group or dist.group.WORLD
+            self.bufs = [symm.empty(N, hidden, dtype=torch.float32, device=device) for _ in range(2)]
+            self.hdls = [symm.rendezvous(b, grp) for b in self.bufs]
+            self.peers = [[h.get_buffer(p, (N, hidden), torch.float32) for p in range(world) if p != rank] for h in self.hdls]
+            self.kind = "symmetric_memory"
+        except Exception as e:                                      # pragma: no cover - depends on the torch build
+            from torch.multiprocessing.reductions import reduce_tensor
+            self.bufs = [torch.empty(N, hidden, dtype=torch.float32, device=device) for _ in range(2)]
+            self.peers = []
+            for b in self.bufs:
+                fn, args = reduce_tensor(b)
+                gathered = [None] * world
+                dist.all_gather_object(gathered, args, group=group)
+                self.peers.append([fn(*gathered[p]) for p in range(world) if p != rank])
+            self._tok = torch.zeros(1, device=device)
+            self.kind = f"cuda_ipc ({type(e).__name__}: {e})"
+
+    def barrier(self, i, group=None):
+        """Cross-rank barrier on the current stream: every rank's layer kernel (and its P2P stores) is done."""
+        if self.hdls is not None:
+            self.hdls[i].barrier()
+        else:
+            dist.all_reduce(self._tok, group=group)
+
+
 def exchange_rows(buf, cuts, rank, world, mode="broadcast", group=None):
     """After a layer: every rank has written buf[cuts[rank]:cuts[rank+1]]; make buf complete everywhere."""
     if world == 1:
@@ -134,10 +170,10 @@ def gpu_synthetic_graph(N, E, seed, device):
 
 def cuda_layer_fn(model):
     """layer_fn for sharded_forward backed by the CUDA kernels (edge block addressed via edge_base)."""
-    def fn(l, h, out, shard, score_out=None):
+    def fn(l, h, out, shard, score_out=None, peer_outs=None):
         model.layer_forward(l, h, shard.rowptr, shard.col, shard.ew, out=out, row_begin=shard.row_begin,
                             row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out,
-                            reuse_long_scan=l > 0)
+                            reuse_long_scan=l > 0, peer_outs=peer_outs)
     return fn
 
 
@@ -150,7 +186,8 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
     del col, ew
     torch.cuda.empty_cache()
-    bufs = [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
+    pb = PeerBuffers(N, HIDDEN, dev, rank, world) if args.exchange == "p2p" else None
+    bufs = pb.bufs if pb else [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
     score = torch.empty(N, device=dev)
     layer = cuda_layer_fn(model)
     K, W = args.steps, max(args.warmup, 3)
@@ -162,9 +199,12 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
         for l in range(LAYERS):
             out = bufs[l & 1]
             last = l == LAYERS - 1
-            layer(l, h, out, shard, score_out=score if last else None)
+            fused = pb is not None and not last
+            layer(l, h, out, shard, score_out=score if last else None, peer_outs=pb.peers[l & 1] if fused else None)
             if i is not None: ev[i][2 * l + 1].record()
-            if not last:                                    # the last layer's rows / scores stay sharded
+            if fused:                                       # rows already written into every peer's buffer by the epilogue
+                pb.barrier(l & 1)
+            elif not last:                                  # the last layer's rows / scores stay sharded
                 exchange_rows(out, shard.cuts, rank, world, args.exchange)
             if i is not None: ev[i][2 * l + 2].record()
             h = out
@@ -218,7 +258,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     return {"metric": "graphsage_t_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph)",
-            "config": dict(workload_config(world), exchange=args.exchange),
+            "config": dict(workload_config(world), exchange=args.exchange + (f" [{pb.kind}]" if pb else "")),
             "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
                          "peak_source": peak_src, "per_layer_compute_ms": [float(v) for v in comp_ms],
