@@ -226,6 +226,9 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     ms_per_step = float(ms) / K
     seg = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(2 * LAYERS)] for i in range(K)]).mean(0)
     comp_ms, comm_ms = seg[0::2], seg[1::2]
+    seg_all = [torch.zeros(2 * LAYERS, device=dev) for _ in range(world)]
+    dist.all_gather(seg_all, torch.tensor(seg, device=dev, dtype=torch.float32))
+    per_rank = [[round(float(v), 4) for v in t_.cpu()] for t_ in seg_all]
     peak, peak_src = measured_peaks()
     e_loc, r_loc = shard.edge_end - shard.edge_base, shard.row_end - shard.row_begin
     dom_bytes = algorithmic_bytes_layer(e_loc, r_loc, HIDDEN)
@@ -263,6 +266,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
                          "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
                          "peak_source": peak_src, "per_layer_compute_ms": [float(v) for v in comp_ms],
                          "per_layer_exchange_ms": [float(v) for v in comm_ms],
+                         "per_rank_segments_ms": per_rank,
                          "exchange_bytes_per_layer": int(N * HIDDEN * 4)},
             "cpu_baseline": None,
             "e2e": e2e,
