@@ -93,7 +93,9 @@ int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int rowptr_is64,
 /* peer_out (host array of n_peers <= 7 device pointers, or NULL): peer-mapped [n_nodes, H] buffers of the other
  * ranks of a 1-D sharded forward (CUDA IPC / symmetric memory over NVLink).  The layer's epilogue stores each
  * output row to `out` AND to every peer buffer: the per-layer embedding exchange is fused into the layer
- * kernel.  The caller provides the cross-rank barrier between layers. */
+ * kernel.  n_peers == -1: peer_out[0] is an NVSwitch MULTICAST address of the buffer on all ranks (this one
+ * included): each element is stored once with multimem.st and replicated by the switch.
+ * The caller provides the cross-rank barrier between layers. */
 
 /* Heads.  score[v] = sigmoid(h_v . node_w + node_b).  If edge_W != NULL also writes
  * proj[v] = (h_v.We[0:H,0], h_v.We[0:H,1], h_v.We[H:2H,0], h_v.We[H:2H,1])  (proj [n,4]). */

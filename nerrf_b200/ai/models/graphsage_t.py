@@ -95,7 +95,7 @@ class GraphSAGE_T(nn.Module):
 
     # -- single layer (used by the sharded forward) ---------------------------------------
     def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None,
-                      edge_base: int = 0, reuse_long_scan: bool = False, peer_outs=None):
+                      edge_base: int = 0, reuse_long_scan: bool = False, peer_outs=None, multicast_ptr: int = 0):
         """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue.
         edge_base: `col` / `edge_w` hold only the edge block [edge_base, edge_base + len) of the graph (a
         1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data.
@@ -116,12 +116,18 @@ class GraphSAGE_T(nn.Module):
             colp, ewp = L.ptr(col), L.ptr(edge_w)
         lws, lws_bytes = self._long_rows_ws(col.numel(), h.device) if self._has_hub_rows(rowptr) else (None, 0)
         algo_flags = ALGOS[self.algo] | (0x100 if reuse_long_scan else 0)
+        if multicast_ptr:                       # NVSwitch multicast address of `out` on every rank (nerrf_b200.dist)
+            import ctypes as C
+            pp = (C.c_void_p * 1)(multicast_ptr); npeers = -1
+        elif peer_outs:
+            pp, npeers = L.ptr_array(peer_outs), len(peer_outs)
+        else:
+            pp, npeers = None, 0
         L.check(L.lib().nerrf_sage_layer_fwd_ex(
             L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
             row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
             L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
-            L.ptr(score_out), L.ptr(lws), lws_bytes, L.ptr_array(peer_outs) if peer_outs else None,
-            len(peer_outs) if peer_outs else 0, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
+            L.ptr(score_out), L.ptr(lws), lws_bytes, pp, npeers, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
         return out
 
     def _has_hub_rows(self, rowptr) -> bool:

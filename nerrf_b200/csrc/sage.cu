@@ -339,7 +339,7 @@ extern "C" int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int r
                                        const float* node_w, float node_b, float* score, void* long_ws,
                                        size_t long_ws_bytes, float* const* peer_out, int n_peers,
                                        nerrf_stream_t stream) {
-    NERRF_REQUIRE(n_peers == 0 || peer_out, "peer_out required with n_peers > 0");
+    NERRF_REQUIRE(n_peers == 0 || peer_out, "peer_out required with n_peers != 0");
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
                           node_b, score, long_ws, long_ws_bytes, peer_out, n_peers, stream);
 }

@@ -243,7 +243,12 @@ constexpr int MAX_PEERS = 7;
 struct Peers {
     float* out[MAX_PEERS];
     int n;
+    float* mc;            // NVSwitch multicast address of the same buffer on ALL ranks (incl. this one), or nullptr:
+                          // one multimem.st per element, replicated by the switch (egress 1x instead of (G-1)x)
 };
+__device__ __forceinline__ void multimem_st(float* addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 
 // ---------------------------------------------------------------- long rows (hub destinations)
 // A destination row with more than LONG_T in-edges would be gathered by ONE warp.  A deterministic pre-pass
@@ -765,10 +770,14 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 if (relu) o = fmaxf(o, 0.f);
                 if (row0 + j < row_end) {
                     const int64_t off = (row0 + j) * UM + f;
-                    out[off] = o;
+                    if (peers.mc) {
+                        multimem_st(peers.mc + off, o);                                 // fused exchange: switch multicast
+                    } else {
+                        out[off] = o;
 #pragma unroll
-                    for (int pr = 0; pr < MAX_PEERS; ++pr)                              // fused exchange: NVLink P2P stores
-                        if (pr < peers.n) peers.out[pr][off] = o;
+                        for (int pr = 0; pr < MAX_PEERS; ++pr)                          // fused exchange: NVLink P2P stores
+                            if (pr < peers.n) peers.out[pr][off] = o;
+                    }
                 }
                 hv[j] = o * my_nw;
             }
@@ -840,9 +849,13 @@ int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t*
                     bool reuse_scan, float* const* peer_out, int n_peers, cudaStream_t st) {
     (void)n_nodes;
     Peers peers{};
-    if (n_peers < 0 || n_peers > MAX_PEERS) { set_error("n_peers must be in 0..%d", MAX_PEERS); return NERRF_ERR_INVALID; }
-    for (int i = 0; i < n_peers; ++i) peers.out[i] = peer_out[i];
-    peers.n = n_peers;
+    if (n_peers == -1) {                      // peer_out[0] is a multicast address covering every rank's buffer
+        peers.mc = peer_out[0];
+    } else {
+        if (n_peers < 0 || n_peers > MAX_PEERS) { set_error("n_peers must be -1 (multicast) or 0..%d", MAX_PEERS); return NERRF_ERR_INVALID; }
+        for (int i = 0; i < n_peers; ++i) peers.out[i] = peer_out[i];
+        peers.n = n_peers;
+    }
 #define GO(FV, NSV)                                                                                                                                                                               \
     return is64 ? launch_umma<FV, NSV, int64_t>(x, (const int64_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, peers, st) \
                 : launch_umma<FV, NSV, int32_t>(x, (const int32_t*)rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, long_ws, long_ws_bytes, reuse_scan, peers, st)

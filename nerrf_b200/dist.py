@@ -59,9 +59,10 @@ class PeerBuffers:
     straight into the peers' buffers (exchange="p2p": the fused compute + collective form) and the only
     per-layer collective left is a tiny cross-rank barrier."""
 
-    def __init__(self, N, hidden, device, rank, world, group=None):
+    def __init__(self, N, hidden, device, rank, world, group=None, multicast=True):
         self.rank, self.world = rank, world
         self.hdls = None
+        self.mc = [0, 0]
         try:
             import torch.distributed._symmetric_memory as symm
             grp = group or dist.group.WORLD
@@ -69,6 +70,15 @@ class PeerBuffers:
             self.hdls = [symm.rendezvous(b, grp) for b in self.bufs]
             self.peers = [[h.get_buffer(p, (N, hidden), torch.float32) for p in range(world) if p != rank] for h in self.hdls]
             self.kind = "symmetric_memory"
+            self.mc = [0, 0]
+            if multicast:
+                try:
+                    mc = [int(h.multicast_ptr) for h in self.hdls]
+                    if all(mc):
+                        self.mc = mc
+                        self.kind = "symmetric_memory + NVSwitch multicast"
+                except Exception:
+                    pass
         except Exception as e:                                      # pragma: no cover - depends on the torch build
             from torch.multiprocessing.reductions import reduce_tensor
             self.bufs = [torch.empty(N, hidden, dtype=torch.float32, device=device) for _ in range(2)]
@@ -170,10 +180,10 @@ def gpu_synthetic_graph(N, E, seed, device):
 
 def cuda_layer_fn(model):
     """layer_fn for sharded_forward backed by the CUDA kernels (edge block addressed via edge_base)."""
-    def fn(l, h, out, shard, score_out=None, peer_outs=None):
+    def fn(l, h, out, shard, score_out=None, peer_outs=None, multicast_ptr=0):
         model.layer_forward(l, h, shard.rowptr, shard.col, shard.ew, out=out, row_begin=shard.row_begin,
                             row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out,
-                            reuse_long_scan=l > 0, peer_outs=peer_outs)
+                            reuse_long_scan=l > 0, peer_outs=peer_outs, multicast_ptr=multicast_ptr)
     return fn
 
 
@@ -186,7 +196,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
     del col, ew
     torch.cuda.empty_cache()
-    pb = PeerBuffers(N, HIDDEN, dev, rank, world) if args.exchange == "p2p" else None
+    pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast") if args.exchange in ("p2p", "multicast") else None
     bufs = pb.bufs if pb else [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
     score = torch.empty(N, device=dev)
     layer = cuda_layer_fn(model)
@@ -200,7 +210,8 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
             out = bufs[l & 1]
             last = l == LAYERS - 1
             fused = pb is not None and not last
-            layer(l, h, out, shard, score_out=score if last else None, peer_outs=pb.peers[l & 1] if fused else None)
+            layer(l, h, out, shard, score_out=score if last else None, peer_outs=pb.peers[l & 1] if fused else None,
+                  multicast_ptr=pb.mc[l & 1] if fused else 0)
             if i is not None: ev[i][2 * l + 1].record()
             if fused:                                       # rows already written into every peer's buffer by the epilogue
                 pb.barrier(l & 1)

@@ -31,19 +31,25 @@ t = lambda a: torch.from_numpy(a).to(dev)
 x, rp, col, ew = t(g.x), t(g.rowptr), t(g.col), t(g.ew)
 h_ref, sc_ref = model(x, rp, col, ew)
 shard = ND.Shard(rp, col, ew, rank, world, device=dev)
-pb = ND.PeerBuffers(200_000, 128, dev, rank, world)
 layer = ND.cuda_layer_fn(model)
-for rep in range(3):
-    h = x
-    for l in range(3):
-        out = pb.bufs[l & 1]
-        layer(l, h, out, shard, peer_outs=pb.peers[l & 1])
-        pb.barrier(l & 1)
-        h = out
-    torch.cuda.synchronize()
-ok = torch.equal(h, h_ref)
-print(f"rank {rank} exchange=p2p [{pb.kind}]: full-matrix bit-exact={ok} max|diff|={float((h - h_ref).abs().max()):.2e}", flush=True)
-assert ok
+for use_mc in (False, True):
+    pb = ND.PeerBuffers(200_000, 128, dev, rank, world, multicast=use_mc)
+    if use_mc and not pb.mc[0]:
+        print(f"rank {rank}: no multicast support on this system ({pb.kind})", flush=True)
+        continue
+    for rep in range(3):
+        h = x
+        for l in range(3):
+            out = pb.bufs[l & 1]
+            out.fill_(-1.0)
+            pb.barrier(l & 1)
+            layer(l, h, out, shard, peer_outs=pb.peers[l & 1], multicast_ptr=pb.mc[l & 1])
+            pb.barrier(l & 1)
+            h = out
+        torch.cuda.synchronize()
+    ok = torch.equal(h, h_ref)
+    print(f"rank {rank} exchange={'multicast' if use_mc else 'p2p'} [{pb.kind}]: full-matrix bit-exact={ok} max|diff|={float((h - h_ref).abs().max()):.2e}", flush=True)
+    assert ok
 # root-parallel MCTS
 rng = np.random.default_rng(2)
 act = Actions(rng.beta(0.5, 0.5, 256), rng.lognormal(0.7, 1.0, 256), np.ones(256))
