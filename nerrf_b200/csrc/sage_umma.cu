@@ -246,8 +246,18 @@ struct Peers {
     float* mc;            // NVSwitch multicast address of the same buffer on ALL ranks (incl. this one), or nullptr:
                           // one multimem.st per element, replicated by the switch (egress 1x instead of (G-1)x)
 };
-__device__ __forceinline__ void multimem_st(float* addr, float v) {
-    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void multimem_st4(float* addr, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// 4x4 transpose across the 4 lanes of a quad: in: lane i holds a[0..3]; out: lane i holds (a[i] of lanes 0,1,2,3).
+__device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, float& a3, int lane) {
+    const bool b0 = lane & 1, b1 = lane & 2;
+    float t;
+    t = b0 ? a0 : a1; t = __shfl_xor_sync(0xffffffffu, t, 1); if (b0) a0 = t; else a1 = t;
+    t = b0 ? a2 : a3; t = __shfl_xor_sync(0xffffffffu, t, 1); if (b0) a2 = t; else a3 = t;
+    t = b1 ? a0 : a2; t = __shfl_xor_sync(0xffffffffu, t, 2); if (b1) a0 = t; else a2 = t;
+    t = b1 ? a1 : a3; t = __shfl_xor_sync(0xffffffffu, t, 2); if (b1) a1 = t; else a3 = t;
 }
 
 // ---------------------------------------------------------------- long rows (hub destinations)
@@ -763,23 +773,36 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(acce_bar(a));                                    // accumulator drained: the MMA may reuse it
-            float hv[32];
+            float hv[32], ov[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float o = __uint_as_float(v[j]) + my_bias;
                 if (relu) o = fmaxf(o, 0.f);
-                if (row0 + j < row_end) {
-                    const int64_t off = (row0 + j) * UM + f;
+                ov[j] = o;
+                hv[j] = o * my_nw;
+            }
+            // Stores: transpose 4x4 inside each lane quad so that a lane owns 4 consecutive features of one row
+            // (16-byte stores; a warp instruction writes four full 128-byte row segments), locally and -- for the
+            // fused exchange -- to the peers' buffers or once through the NVSwitch multicast address.
+            const int qi = lane & 3;                                      // row within the block of 4
+            const int fq = warp * 32 + (lane & ~3);                       // first of this lane's 4 features
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float a0 = ov[4 * r], a1 = ov[4 * r + 1], a2 = ov[4 * r + 2], a3 = ov[4 * r + 3];
+                quad_transpose(a0, a1, a2, a3, lane);
+                const int64_t row = row0 + 4 * r + qi;
+                if (row < row_end) {
+                    const int64_t off = row * UM + fq;
+                    const float4 val = make_float4(a0, a1, a2, a3);
                     if (peers.mc) {
-                        multimem_st(peers.mc + off, o);                                 // fused exchange: switch multicast
+                        multimem_st4(peers.mc + off, val);                              // fused exchange: switch multicast
                     } else {
-                        out[off] = o;
+                        *reinterpret_cast<float4*>(out + off) = val;
 #pragma unroll
                         for (int pr = 0; pr < MAX_PEERS; ++pr)                          // fused exchange: NVLink P2P stores
-                            if (pr < peers.n) peers.out[pr][off] = o;
+                            if (pr < peers.n) *reinterpret_cast<float4*>(peers.out[pr] + off) = val;
                     }
                 }
-                hv[j] = o * my_nw;
             }
             if (node_w) {
                 // fused node head: score[row] = sigmoid(h[row,:] . node_w + node_b)
