@@ -781,26 +781,34 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 ov[j] = o;
                 hv[j] = o * my_nw;
             }
-            // Stores: transpose 4x4 inside each lane quad so that a lane owns 4 consecutive features of one row
-            // (16-byte stores; a warp instruction writes four full 128-byte row segments), locally and -- for the
-            // fused exchange -- to the peers' buffers or once through the NVSwitch multicast address.
-            const int qi = lane & 3;                                      // row within the block of 4
-            const int fq = warp * 32 + (lane & ~3);                       // first of this lane's 4 features
+            if (peers.n == 0 && !peers.mc) {
+                // single GPU: thread = feature, 32 row stores of 128 B per warp (no extra shuffles: the epilogue
+                // shares issue slots with the gather warps)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float a0 = ov[4 * r], a1 = ov[4 * r + 1], a2 = ov[4 * r + 2], a3 = ov[4 * r + 3];
-                quad_transpose(a0, a1, a2, a3, lane);
-                const int64_t row = row0 + 4 * r + qi;
-                if (row < row_end) {
-                    const int64_t off = row * UM + fq;
-                    const float4 val = make_float4(a0, a1, a2, a3);
-                    if (peers.mc) {
-                        multimem_st4(peers.mc + off, val);                              // fused exchange: switch multicast
-                    } else {
-                        *reinterpret_cast<float4*>(out + off) = val;
+                for (int j = 0; j < 32; ++j)
+                    if (row0 + j < row_end) out[(row0 + j) * UM + f] = ov[j];
+            } else {
+                // fused exchange: transpose 4x4 inside each lane quad so that a lane owns 4 consecutive features of
+                // one row (16-byte stores; a warp instruction writes four full 128-byte row segments) -- locally and
+                // to every peer's buffer over NVLink, or once through the NVSwitch multicast address.
+                const int qi = lane & 3;                                  // row within the block of 4
+                const int fq = warp * 32 + (lane & ~3);                   // first of this lane's 4 features
 #pragma unroll
-                        for (int pr = 0; pr < MAX_PEERS; ++pr)                          // fused exchange: NVLink P2P stores
-                            if (pr < peers.n) *reinterpret_cast<float4*>(peers.out[pr] + off) = val;
+                for (int r = 0; r < 8; ++r) {
+                    float a0 = ov[4 * r], a1 = ov[4 * r + 1], a2 = ov[4 * r + 2], a3 = ov[4 * r + 3];
+                    quad_transpose(a0, a1, a2, a3, lane);
+                    const int64_t row = row0 + 4 * r + qi;
+                    if (row < row_end) {
+                        const int64_t off = row * UM + fq;
+                        const float4 val = make_float4(a0, a1, a2, a3);
+                        if (peers.mc) {
+                            multimem_st4(peers.mc + off, val);
+                        } else {
+                            *reinterpret_cast<float4*>(out + off) = val;
+#pragma unroll
+                            for (int pr = 0; pr < MAX_PEERS; ++pr)
+                                if (pr < peers.n) *reinterpret_cast<float4*>(peers.out[pr] + off) = val;
+                        }
                     }
                 }
             }
