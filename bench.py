@@ -374,9 +374,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "umma", "umma2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "multicast", "allgather", "broadcast", "allreduce"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-all", "multicast", "allgather", "broadcast", "allreduce"],
                     help="N>1: per-layer embedding exchange: p2p = fused into the layer kernel (epilogue stores to "
-                         "peer-mapped buffers over NVLink); allgather / broadcast / allreduce = NCCL collectives")
+                         "peer-mapped buffers over NVLink, only the rows a peer references); p2p-all = same, every row "
+                         "to every peer; multicast = NVSwitch multimem.st; allgather / broadcast / allreduce = NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

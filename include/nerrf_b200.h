@@ -89,11 +89,12 @@ int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int rowptr_is64,
                             int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int H,
                             int relu, int algo, const float* node_w, float node_b, float* score,
                             void* long_ws, size_t long_ws_bytes, float* const* peer_out, int n_peers,
-                            nerrf_stream_t stream);
+                            const uint8_t* peer_need, nerrf_stream_t stream);
 /* peer_out (host array of n_peers <= 7 device pointers, or NULL): peer-mapped [n_nodes, H] buffers of the other
  * ranks of a 1-D sharded forward (CUDA IPC / symmetric memory over NVLink).  The layer's epilogue stores each
  * output row to `out` AND to every peer buffer: the per-layer embedding exchange is fused into the layer
- * kernel.  n_peers == -1: peer_out[0] is an NVSwitch MULTICAST address of the buffer on all ranks (this one
+ * kernel.  peer_need (device uint8 [n_nodes], or NULL): bit i set <=> peer_out[i]'s rank references that row as
+ * a source, so only the rows a peer actually reads are sent to it.  n_peers == -1: peer_out[0] is an NVSwitch MULTICAST address of the buffer on all ranks (this one
  * included): each element is stored once with multimem.st and replicated by the switch.
  * The caller provides the cross-rank barrier between layers. */
 

@@ -31,7 +31,7 @@ SIGNATURES = {
     "nerrf_sage_long_rows_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "nerrf_sage_layer_fwd_ex": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64,
                                           C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp, C.c_size_t,
-                                          C.POINTER(vp), C.c_int, vp]),
+                                          C.POINTER(vp), C.c_int, vp, vp]),
     "nerrf_sage_node_head": (C.c_int, [vp, vp, C.c_float, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "nerrf_sage_edge_head": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, vp]),
     "nerrf_sage_forward": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int,

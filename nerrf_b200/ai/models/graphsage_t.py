@@ -95,14 +95,16 @@ class GraphSAGE_T(nn.Module):
 
     # -- single layer (used by the sharded forward) ---------------------------------------
     def layer_forward(self, l: int, h, rowptr, col, edge_w, out=None, row_begin=0, row_end=None, relu=True, score_out=None,
-                      edge_base: int = 0, reuse_long_scan: bool = False, peer_outs=None, multicast_ptr: int = 0):
+                      edge_base: int = 0, reuse_long_scan: bool = False, peer_outs=None, multicast_ptr: int = 0,
+                      peer_need=None):
         """One fused layer.  score_out (fp32 [N]) fuses the node head into the layer's epilogue.
         edge_base: `col` / `edge_w` hold only the edge block [edge_base, edge_base + len) of the graph (a
         1-D shard); rowptr keeps absolute edge offsets, so the pointers are shifted instead of the data.
         reuse_long_scan: the previous layer_forward call on this model used the SAME graph and row range, so
         the hub-row scan held in the scratch is still valid (layers 2..L of one forward).
         peer_outs: list of peer-mapped [N, H] tensors (other ranks' `out` buffers): the epilogue also stores
-        the produced rows there (fused per-layer exchange of the sharded forward, nerrf_b200.dist)."""
+        the produced rows there (fused per-layer exchange of the sharded forward, nerrf_b200.dist).
+        peer_need: uint8 [N], bit i set <=> peer_outs[i]'s rank reads that row as a source (send only those)."""
         self._check_graph(h, rowptr, col, edge_w)
         N = h.shape[0]
         row_end = N if row_end is None else row_end
@@ -127,7 +129,8 @@ class GraphSAGE_T(nn.Module):
             L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
             row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
             L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
-            L.ptr(score_out), L.ptr(lws), lws_bytes, pp, npeers, L.current_stream_ptr()), "nerrf_sage_layer_fwd_ex")
+            L.ptr(score_out), L.ptr(lws), lws_bytes, pp, npeers, L.ptr(peer_need), L.current_stream_ptr()),
+            "nerrf_sage_layer_fwd_ex")
         return out
 
     def _has_hub_rows(self, rowptr) -> bool:

@@ -14,7 +14,7 @@ int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t*
                     const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin,
                     int64_t row_end, int F, int relu, int nsplit, const float* node_w, float node_b, float* score,
                     void* long_ws, size_t long_ws_bytes, bool reuse_scan, float* const* peer_out, int n_peers,
-                    cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
+                    const uint8_t* peer_need, cudaStream_t st);   // sage_umma.cu (node_w != NULL: node head fused into the epilogue)
 bool sage_umma_available();
 
 // ------------------------------------------------------------------------------------------
@@ -282,7 +282,7 @@ static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, c
                           const float* W, const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end,
                           int F, int H, int relu, int algo, const float* node_w, float node_b, float* score,
                           void* long_ws, size_t long_ws_bytes, float* const* peer_out, int n_peers,
-                          nerrf_stream_t stream) {
+                          const uint8_t* peer_need, nerrf_stream_t stream) {
     int rc = check_graph_args(x, rowptr, col, ew, n_nodes, row_begin, row_end);
     if (rc) return rc;
     NERRF_REQUIRE(W && b && out, "null weight/output pointer");
@@ -298,7 +298,7 @@ static int layer_fwd_impl(const float* x, const void* rowptr, int rowptr_is64, c
     if (algo == NERRF_SAGE_ALGO_UMMA || algo == NERRF_SAGE_ALGO_UMMA2)
         return sage_layer_umma(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, relu,
                                algo == NERRF_SAGE_ALGO_UMMA ? 3 : 2, node_w, node_b, score, long_ws, long_ws_bytes,
-                               reuse_scan, peer_out, n_peers, st);
+                               reuse_scan, peer_out, n_peers, peer_need, st);
     NERRF_REQUIRE(n_peers == 0, "the fused peer exchange needs the tcgen05 layer (algo umma)");
     NERRF_REQUIRE(algo == NERRF_SAGE_ALGO_FFMA, "unknown algo %d", algo);
     rc = rowptr_is64
@@ -313,7 +313,7 @@ extern "C" int nerrf_sage_layer_fwd(const float* x, const void* rowptr, int rowp
                                     int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
                                     nerrf_stream_t stream) {
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo,
-                          nullptr, 0.f, nullptr, nullptr, 0, nullptr, 0, stream);
+                          nullptr, 0.f, nullptr, nullptr, 0, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
@@ -322,7 +322,7 @@ extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int
                                          const float* node_w, float node_b, float* score, nerrf_stream_t stream) {
     NERRF_REQUIRE(node_w && score, "null head pointer");
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
-                          node_b, score, nullptr, 0, nullptr, 0, stream);
+                          node_b, score, nullptr, 0, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int nerrf_sage_long_rows_workspace_bytes(int64_t n_edges, size_t* bytes) {
@@ -338,10 +338,10 @@ extern "C" int nerrf_sage_layer_fwd_ex(const float* x, const void* rowptr, int r
                                        int64_t row_begin, int64_t row_end, int F, int H, int relu, int algo,
                                        const float* node_w, float node_b, float* score, void* long_ws,
                                        size_t long_ws_bytes, float* const* peer_out, int n_peers,
-                                       nerrf_stream_t stream) {
+                                       const uint8_t* peer_need, nerrf_stream_t stream) {
     NERRF_REQUIRE(n_peers == 0 || peer_out, "peer_out required with n_peers != 0");
     return layer_fwd_impl(x, rowptr, rowptr_is64, col, ew, W, b, out, n_nodes, row_begin, row_end, F, H, relu, algo, node_w,
-                          node_b, score, long_ws, long_ws_bytes, peer_out, n_peers, stream);
+                          node_b, score, long_ws, long_ws_bytes, peer_out, n_peers, peer_need, stream);
 }
 
 extern "C" int nerrf_sage_node_head(const float* h, const float* node_w, float node_b, float* score,
@@ -401,7 +401,7 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
         int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1,
                                 (algo & 0xFF) | (l > 0 ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0),
                                 (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
-                                long_ws, long_ws_bytes, nullptr, 0, stream);
+                                long_ws, long_ws_bytes, nullptr, 0, nullptr, stream);
         if (rc) return rc;
         in = o;
         F = hidden;

@@ -243,6 +243,8 @@ constexpr int MAX_PEERS = 7;
 struct Peers {
     float* out[MAX_PEERS];
     int n;
+    const uint8_t* need;  // optional [n_nodes]: bit pr set <=> peer slot pr references this row as a source; rows a
+                          // peer never reads are not sent to it (nullptr: send every row to every peer)
     float* mc;            // NVSwitch multicast address of the same buffer on ALL ranks (incl. this one), or nullptr:
                           // one multimem.st per element, replicated by the switch (egress 1x instead of (G-1)x)
 };
@@ -805,9 +807,10 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                             multimem_st4(peers.mc + off, val);
                         } else {
                             *reinterpret_cast<float4*>(out + off) = val;
+                            const unsigned need = peers.need ? (unsigned)__ldg(peers.need + row) : 0xFFu;
 #pragma unroll
                             for (int pr = 0; pr < MAX_PEERS; ++pr)
-                                if (pr < peers.n) *reinterpret_cast<float4*>(peers.out[pr] + off) = val;
+                                if (pr < peers.n && ((need >> pr) & 1u)) *reinterpret_cast<float4*>(peers.out[pr] + off) = val;
                         }
                     }
                 }
@@ -877,9 +880,10 @@ bool sage_umma_available() { return true; }
 int sage_layer_umma(const float* x, const void* rowptr, int is64, const int32_t* col, const float* ew, const float* W,
                     const float* b, float* out, int64_t n_nodes, int64_t row_begin, int64_t row_end, int F, int relu,
                     int nsplit, const float* node_w, float node_b, float* score, void* long_ws, size_t long_ws_bytes,
-                    bool reuse_scan, float* const* peer_out, int n_peers, cudaStream_t st) {
+                    bool reuse_scan, float* const* peer_out, int n_peers, const uint8_t* peer_need, cudaStream_t st) {
     (void)n_nodes;
     Peers peers{};
+    peers.need = peer_need;
     if (n_peers == -1) {                      // peer_out[0] is a multicast address covering every rank's buffer
         peers.mc = peer_out[0];
     } else {

@@ -91,6 +91,28 @@ class PeerBuffers:
             self._tok = torch.zeros(1, device=device)
             self.kind = f"cuda_ipc ({type(e).__name__}: {e})"
 
+    def build_need_mask(self, shard: "Shard", N, group=None):
+        """uint8 [N]: bit i set <=> the rank behind peer slot i references that row as a SOURCE in its edge block.
+        Graph preprocessing (once per graph): each rank marks the sources of its edges, the bitmaps are
+        all-gathered, and every rank keeps the bits of its own destination-row range."""
+        dev = shard.col.device
+        mine = torch.zeros(N, dtype=torch.uint8, device=dev)
+        mine[shard.col.long()] = 1
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allb, mine, group=group)
+        mask = torch.zeros(N, dtype=torch.uint8, device=dev)
+        slot = 0
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            mask |= allb[p] << slot
+            slot += 1
+        self.need = mask
+        rb, re = shard.row_begin, shard.row_end
+        sent = sum(int(((mask[rb:re] >> s_) & 1).sum()) for s_ in range(self.world - 1))
+        self.need_fraction = sent / max(1, (re - rb) * (self.world - 1))
+        return mask
+
     def barrier(self, i, group=None):
         """Cross-rank barrier on the current stream: every rank's layer kernel (and its P2P stores) is done."""
         if self.hdls is not None:
@@ -180,10 +202,11 @@ def gpu_synthetic_graph(N, E, seed, device):
 
 def cuda_layer_fn(model):
     """layer_fn for sharded_forward backed by the CUDA kernels (edge block addressed via edge_base)."""
-    def fn(l, h, out, shard, score_out=None, peer_outs=None, multicast_ptr=0):
+    def fn(l, h, out, shard, score_out=None, peer_outs=None, multicast_ptr=0, peer_need=None):
         model.layer_forward(l, h, shard.rowptr, shard.col, shard.ew, out=out, row_begin=shard.row_begin,
                             row_end=shard.row_end, edge_base=shard.edge_base, score_out=score_out,
-                            reuse_long_scan=l > 0, peer_outs=peer_outs, multicast_ptr=multicast_ptr)
+                            reuse_long_scan=l > 0, peer_outs=peer_outs, multicast_ptr=multicast_ptr,
+                            peer_need=peer_need)
     return fn
 
 
@@ -196,7 +219,8 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
     del col, ew
     torch.cuda.empty_cache()
-    pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast") if args.exchange in ("p2p", "multicast") else None
+    pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast") if args.exchange in ("p2p", "p2p-all", "multicast") else None
+    need = pb.build_need_mask(shard, N) if args.exchange == "p2p" else None
     bufs = pb.bufs if pb else [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
     score = torch.empty(N, device=dev)
     layer = cuda_layer_fn(model)
@@ -211,7 +235,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
             last = l == LAYERS - 1
             fused = pb is not None and not last
             layer(l, h, out, shard, score_out=score if last else None, peer_outs=pb.peers[l & 1] if fused else None,
-                  multicast_ptr=pb.mc[l & 1] if fused else 0)
+                  multicast_ptr=pb.mc[l & 1] if fused else 0, peer_need=need if fused else None)
             if i is not None: ev[i][2 * l + 1].record()
             if fused:                                       # rows already written into every peer's buffer by the epilogue
                 pb.barrier(l & 1)
@@ -272,7 +296,8 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     return {"metric": "graphsage_t_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph)",
-            "config": dict(workload_config(world), exchange=args.exchange + (f" [{pb.kind}]" if pb else "")),
+            "config": dict(workload_config(world), exchange=args.exchange + (f" [{pb.kind}]" if pb else "") +
+                           (f", rows sent to a peer only if it references them ({100 * pb.need_fraction:.0f}% of row x peer pairs)" if need is not None else "")),
             "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
                          "peak_source": peak_src, "per_layer_compute_ms": [float(v) for v in comp_ms],

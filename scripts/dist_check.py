@@ -32,6 +32,22 @@ x, rp, col, ew = t(g.x), t(g.rowptr), t(g.col), t(g.ew)
 h_ref, sc_ref = model(x, rp, col, ew)
 shard = ND.Shard(rp, col, ew, rank, world, device=dev)
 layer = ND.cuda_layer_fn(model)
+# needed-rows variant: only rows a peer references are sent; every rank's OWN rows of the final layer must match
+pb = ND.PeerBuffers(200_000, 128, dev, rank, world, multicast=False)
+need = pb.build_need_mask(shard, 200_000)
+for rep in range(2):
+    h = x
+    for l in range(3):
+        out = pb.bufs[l & 1]
+        out.fill_(float("nan")); pb.barrier(l & 1)
+        layer(l, h, out, shard, peer_outs=pb.peers[l & 1], peer_need=need)
+        pb.barrier(l & 1)
+        h = out
+    torch.cuda.synchronize()
+ok = torch.equal(h[shard.row_begin:shard.row_end], h_ref[shard.row_begin:shard.row_end])
+print(f"rank {rank} exchange=p2p needed-rows ({100 * pb.need_fraction:.0f}% of row x peer pairs sent): own rows bit-exact={ok}", flush=True)
+assert ok
+del pb
 for use_mc in (False, True):
     pb = ND.PeerBuffers(200_000, 128, dev, rank, world, multicast=use_mc)
     if use_mc and not pb.mc[0]:
