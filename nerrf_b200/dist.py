@@ -180,8 +180,11 @@ def root_parallel_search(search_fn, rank, world, group=None):
 
 
 # ----------------------------------------------------------------------------------------------- GPU side
-def gpu_synthetic_graph(N, E, seed, device):
-    """Same distribution as graph.synthetic_graph (dst ~ U, src = floor(N u^3), t ~ U[0,60), conf ~ U[.5,1]),
+def gpu_synthetic_graph(N, E, seed, device, relabel=False):
+    """relabel=True applies a random vertex relabeling (an isomorphic graph): the hub nodes, which every shard
+    references, are then spread evenly over the row blocks instead of all living in rank 0's block -- the usual
+    partitioning pre-step that balances the per-rank exchange volume.
+    Same distribution as graph.synthetic_graph (dst ~ U, src = floor(N u^3), t ~ U[0,60), conf ~ U[.5,1]),
     generated on the GPU so every rank can build the N x 10M-edge graph in about a second.  The CUDA Philox
     generator is deterministic per (seed, call order), so all ranks hold the same graph."""
     gen = torch.Generator(device=device).manual_seed(seed)
@@ -189,6 +192,9 @@ def gpu_synthetic_graph(N, E, seed, device):
     src = (N * torch.rand(E, generator=gen, device=device, dtype=torch.float64) ** 3).long().clamp_(max=N - 1)
     t = torch.rand(E, generator=gen, device=device) * G.WINDOW
     conf = 0.5 + 0.5 * torch.rand(E, generator=gen, device=device)
+    if relabel:
+        perm = torch.randperm(N, generator=gen, device=device)
+        src, dst = perm[src], perm[dst]
     order = torch.argsort(t, stable=True)
     order = order[torch.argsort(dst[order], stable=True)]
     src, dst, t, conf = src[order], dst[order], t[order], conf[order]
@@ -215,7 +221,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     """bench.py's N > 1 arm (weak scaling: N x (1M nodes, 10M edges), one exchange per layer)."""
     from bench import N_NODES, N_EDGES, HIDDEN, LAYERS, F_IN
     N, E = N_NODES * world, N_EDGES * world
-    rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev)
+    rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, relabel=True)
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
     del col, ew
     torch.cuda.empty_cache()
@@ -295,7 +301,8 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     traffic = json.load(open(tp)).get("sage_layer_F128_dram_bytes_per_launch") if os.path.exists(tp) else None
     return {"metric": "graphsage_t_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph)",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph, random vertex relabeling for shard balance)",
             "config": dict(workload_config(world), exchange=args.exchange + (f" [{pb.kind}]" if pb else "") +
                            (f", rows sent to a peer only if it references them ({100 * pb.need_fraction:.0f}% of row x peer pairs)" if need is not None else "")),
             "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
