@@ -223,10 +223,23 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
     N, E = N_NODES * world, N_EDGES * world
     rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, relabel=True)
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
-    del col, ew
+    shard_src_col, shard_src_ew = col, ew           # kept only until the exchange mode is settled (fallback re-shards)
+    pb, need, exchange_note = None, None, ""
+    if args.exchange in ("p2p", "p2p-all", "multicast"):
+        try:
+            pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast")
+            need = pb.build_need_mask(shard, N) if args.exchange == "p2p" else None
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                      # no peer mapping on this system: fall back to the NCCL exchange
+            pb, need, ok = None, None, torch.zeros(1, device=dev)
+            exchange_note = f" (peer mapping failed: {type(e).__name__}; fell back to allgather)"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if float(ok) == 0.0:
+            pb, need = None, None
+            args.exchange = "allgather"
+            shard = Shard(rowptr, shard_src_col, shard_src_ew, rank, world, device=dev, cut="rows")
+    del shard_src_col, shard_src_ew, col, ew
     torch.cuda.empty_cache()
-    pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast") if args.exchange in ("p2p", "p2p-all", "multicast") else None
-    need = pb.build_need_mask(shard, N) if args.exchange == "p2p" else None
     bufs = pb.bufs if pb else [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
     score = torch.empty(N, device=dev)
     layer = cuda_layer_fn(model)
@@ -303,7 +316,7 @@ def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, al
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph, random vertex relabeling for shard balance)",
-            "config": dict(workload_config(world), exchange=args.exchange + (f" [{pb.kind}]" if pb else "") +
+            "config": dict(workload_config(world), exchange=args.exchange + exchange_note + (f" [{pb.kind}]" if pb else "") +
                            (f", rows sent to a peer only if it references them ({100 * pb.need_fraction:.0f}% of row x peer pairs)" if need is not None else "")),
             "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
