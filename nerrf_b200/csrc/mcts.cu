@@ -17,10 +17,7 @@
 //   backup   CTA 0: adjacent-pairs tree sum of val -> path edges; all CTAs: per-first-action
 //            child statistics of the leaf (fixed ascending-r order)
 //   grid barrier
-#include <cooperative_groups.h>
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace nerrf {
 
@@ -464,11 +461,7 @@ extern "C" int nerrf_reward_score(const uint32_t* states, int64_t B, const float
     if (NW == 1) reward_score_kernel<1><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
     else if (NW == 2) reward_score_kernel<2><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
     else {
-        static bool set = false;
-        if (!set) {
-            NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
-        }
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         reward_score_kernel<4><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
     }
     return launch_status("reward_score_kernel");

@@ -212,7 +212,10 @@ template <int F, typename RP>
 static int launch_ffma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W,
                        const float* b, float* out, int64_t row_begin, int64_t row_end, int relu, cudaStream_t st) {
     using C = FfmaCfg<F>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];          // function attributes are per device
     if (!attr_set) {
         NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_ffma_kernel<F, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)C::smem));

@@ -1,4 +1,6 @@
-// K1 inner loop: weighted-mean gather of one CSR row by one warp.
+// K1 inner loop: weighted-mean gather of one CSR row by one warp.  Used by the fp32
+// cross-check layer, the standalone aggregate and the hub-row chunk pre-pass; the tcgen05 layer has its own
+// cp.async ring pipeline (sage_umma.cu).
 //
 // A source row is F floats = F/4 float4.  LPR = F/4 lanes cover one source row with one 16-byte
 // load each, so a warp fetches G = 32/LPR source rows per load instruction (F=128: 1 row of
@@ -11,16 +13,13 @@
 
 namespace nerrf {
 
-// `pre_c` / `pre_w`: this lane's col / ew for edge e0 + lane, already loaded by the caller (software
-// pipelining: the caller fetches them one row ahead so the only exposed latency is the x rows).
-//
 // 2*UH load instructions (2*UH*G source rows) are issued BEFORE anything is consumed.  Weights are
 // re-broadcast at consume time instead of being held in registers.
 // wsum_out != nullptr: return the UNNORMALISED weighted sum and store the weight sum (used for chunk partials).
-template <int F, bool PRE = false, int UH = 0>
+template <int F, int UH = 0>
 __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const int32_t* __restrict__ col,
                                               const float* __restrict__ ew, int64_t e0, int64_t e1, int lane,
-                                              int pre_c = 0, float pre_w = 0.f, float* wsum_out = nullptr) {
+                                              float* wsum_out = nullptr) {
     constexpr int LPR = F / 4;        // lanes per source row
     constexpr int G = 32 / LPR;       // source rows per load instruction
     constexpr int U = UH > 0 ? UH : ((G == 1) ? 4 : 2);   // load instructions per half batch
@@ -33,10 +32,7 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const 
         const int n = (int)((e1 - base) < 32 ? (e1 - base) : 32);
         int my_c = 0;
         float my_w = 0.f;
-        if (PRE && base == e0) {
-            my_c = pre_c;
-            my_w = pre_w;
-        } else if (lane < n) {
+        if (lane < n) {
             my_c = __ldg(col + base + lane);
             my_w = __ldg(ew + base + lane);
         }
@@ -73,71 +69,5 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const 
     return acc;
 }
 
-
-// Edge-block variant used by the tcgen05 kernel: the tile's col / ew live in SHARED memory (staged
-// asynchronously by a loader warp), indexed relative to the tile's first edge; edges past the staged
-// capacity `cap` are read from global (`colg` / `ewg` point at the tile's first edge).  All 2*UH load
-// instructions of a batch are issued before anything is consumed (one exposed latency for up to
-// 2*UH*G in-edges); only the consumption of the second half is skipped for short rows.
-template <int F, int UH>
-__device__ __forceinline__ float4 gather_row_staged(const float* __restrict__ x, const int32_t* __restrict__ col_s,
-                                                     const float* __restrict__ ew_s, int cap,
-                                                     const int32_t* __restrict__ colg, const float* __restrict__ ewg,
-                                                     int e0, int e1, int lane) {
-    constexpr int LPR = F / 4, G = 32 / LPR, U = UH;
-    const int g = lane / LPR, sub = lane % LPR;
-    const float* xs = x + 4 * sub;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wpart = 0.f;
-    for (int base = e0; base < e1; base += 32) {
-        const int n = (e1 - base) < 32 ? (e1 - base) : 32;
-        int my_c = 0;
-        float my_w = 0.f;
-        if (lane < n) {
-            const int k = base + lane;
-            if (k < cap) { my_c = col_s[k]; my_w = ew_s[k]; }
-            else { my_c = __ldg(colg + k); my_w = __ldg(ewg + k); }
-        }
-        wpart += my_w;
-        for (int j = 0; j < n; j += 2 * G * U) {
-            float4 v[2 * U];
-#pragma unroll
-            for (int u = 0; u < 2 * U; ++u) {
-                const int idx = j + u * G + g;
-                const int c = __shfl_sync(0xffffffffu, my_c, idx & 31);
-                v[u] = (idx < n) ? ldg4(xs + (int64_t)c * F) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = j + u * G + g;
-                float w = __shfl_sync(0xffffffffu, my_w, idx & 31);
-                w = (idx < n) ? w : 0.f;
-                acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y);
-                acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
-            }
-            if ((n - j) > G * U) {
-#pragma unroll
-                for (int u = U; u < 2 * U; ++u) {
-                    const int idx = j + u * G + g;
-                    float w = __shfl_sync(0xffffffffu, my_w, idx & 31);
-                    w = (idx < n) ? w : 0.f;
-                    acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y);
-                    acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    const float wsum = warp_sum(wpart);
-    const float inv = 1.0f / fmaxf(wsum, 1e-12f);
-    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-    return acc;
-}
 
 }  // namespace nerrf

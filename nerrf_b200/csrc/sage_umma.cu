@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) long_chunk_kernel(const float* __restrict
         if (b > c1) b = c1;
         float wsum = 0.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a < b) acc = gather_row<F>(x, col, ew, a, b, lane, 0, 0.f, &wsum);
+        if (a < b) acc = gather_row<F>(x, col, ew, a, b, lane, &wsum);
         if (lane < LPR) s_acc[warp][lane] = acc;
         if (lane == 0) s_w[warp] = wsum;
         __syncthreads();
@@ -842,7 +842,10 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
                 void* long_ws, size_t long_ws_bytes, bool reuse_scan, const Peers& peers, cudaStream_t st) {
     using C = UmmaCfg<F, NS>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];          // function attributes are per device
     if (!attr_set) {
         NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));

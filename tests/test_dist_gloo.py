@@ -36,6 +36,19 @@ def _worker(rank, world, port, exchange, q):
         h, score = ND.sharded_forward(layer_fn, 3, t(g.x), shard, 128, exchange=exchange, head_fn=head_fn)
         hw, scw = S.forward(P, t(g.x), t(g.rowptr), full_col, full_ew)
         ok = torch.allclose(h, hw, rtol=1e-5, atol=1e-6) and torch.allclose(score, scw[shard.row_begin:shard.row_end], atol=1e-6)
+        # need mask of the fused exchange: bit (peer slot) set <=> that peer's edge block references the row
+        pb = ND.PeerBuffers.__new__(ND.PeerBuffers); pb.rank, pb.world = rank, world
+        mask = pb.build_need_mask(shard, g.num_nodes).numpy()
+        cuts = shard.cuts
+        slot = 0
+        for p_ in range(world):
+            if p_ == rank:
+                continue
+            e0, e1 = int(g.rowptr[cuts[p_]]), int(g.rowptr[cuts[p_ + 1]])
+            want_bits = np.zeros(g.num_nodes, bool); want_bits[g.col[e0:e1]] = True
+            ok = ok and np.array_equal(((mask >> slot) & 1).astype(bool), want_bits)
+            slot += 1
+        ok = ok and 0.0 < pb.need_fraction <= 1.0
         # root-parallel MCTS merge: every rank ends with the same merged statistics
         rng = np.random.default_rng(0)
         p = rng.beta(0.5, 0.5, 40).astype(np.float32); size = rng.lognormal(0.7, 1, 40).astype(np.float32)
