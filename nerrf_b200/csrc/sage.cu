@@ -377,32 +377,6 @@ extern "C" int nerrf_sage_edge_head(const float* proj, const void* rowptr, int r
     return launch_status("sage_edge_head_kernel");
 }
 
-// Layers [l0, l1) of the forward.  `in0` / `F0` = input of layer l0.  Layer l writes h_out when (L-1-l) is even, else
-// the ping-pong workspace; the node head is fused into layer L-1.  row range = all rows.
-static int forward_range(const float* in0, int F0, int l0, int l1, const void* rowptr, int rowptr_is64, const int32_t* col,
-                         const float* ew, int64_t n_nodes, int hidden, int num_layers, const float* const* W,
-                         const float* const* b, const float* node_w, float node_b, float* h_out, float* score_out,
-                         float* workspace, size_t workspace_bytes, int algo, bool scan_valid, nerrf_stream_t stream) {
-    // workspace beyond the [n_nodes, hidden] ping-pong buffer (if any) is the hub-row pre-aggregation scratch
-    const size_t pp = num_layers > 1 ? (((size_t)n_nodes * hidden * sizeof(float) + 255) & ~(size_t)255) : 0;
-    void* long_ws = (workspace && workspace_bytes > pp + 8192) ? (void*)((unsigned char*)workspace + pp) : nullptr;
-    const size_t long_ws_bytes = long_ws ? workspace_bytes - pp : 0;
-    const float* in = in0;
-    int F = F0;
-    for (int l = l0; l < l1; ++l) {
-        float* o = ((num_layers - 1 - l) % 2 == 0) ? h_out : workspace;
-        const bool last = l == num_layers - 1;
-        int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1,
-                                (algo & 0xFF) | ((l > l0 || scan_valid) ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0),
-                                (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
-                                long_ws, long_ws_bytes, nullptr, 0, nullptr, stream);
-        if (rc) return rc;
-        in = o;
-        F = hidden;
-    }
-    return NERRF_OK;
-}
-
 extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr_is64, const int32_t* col,
                                   const float* ew, int64_t n_nodes, int f_in, int hidden, int num_layers,
                                   const float* const* W, const float* const* b, const float* node_w, float node_b,
@@ -418,8 +392,24 @@ extern "C" int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr
         }
     }
     if (score_out) NERRF_REQUIRE(node_w, "node_w required for score_out");
-    return forward_range(x, f_in, 0, num_layers, rowptr, rowptr_is64, col, ew, n_nodes, hidden, num_layers, W, b, node_w,
-                         node_b, h_out, score_out, workspace, workspace_bytes, algo, false, stream);
+    // workspace beyond the [n_nodes, hidden] ping-pong buffer (if any) is the hub-row pre-aggregation scratch
+    const size_t pp = num_layers > 1 ? (((size_t)n_nodes * hidden * sizeof(float) + 255) & ~(size_t)255) : 0;
+    void* long_ws = (workspace && workspace_bytes > pp + 8192) ? (void*)((unsigned char*)workspace + pp) : nullptr;
+    const size_t long_ws_bytes = long_ws ? workspace_bytes - pp : 0;
+    const float* in = x;
+    int F = f_in;
+    for (int l = 0; l < num_layers; ++l) {
+        float* o = ((num_layers - 1 - l) % 2 == 0) ? h_out : workspace;
+        const bool last = l == num_layers - 1;
+        int rc = layer_fwd_impl(in, rowptr, rowptr_is64, col, ew, W[l], b[l], o, n_nodes, 0, n_nodes, F, hidden, 1,
+                                (algo & 0xFF) | (l > 0 ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0),
+                                (last && score_out) ? node_w : nullptr, node_b, (last && score_out) ? score_out : nullptr,
+                                long_ws, long_ws_bytes, nullptr, 0, nullptr, stream);
+        if (rc) return rc;
+        in = o;
+        F = hidden;
+    }
+    return NERRF_OK;
 }
 
 // ------------------------------------------------------------------------------------------ session
@@ -437,8 +427,7 @@ struct nerrf_sage_session {
     float* Wd[64];
     float* bd[64];
     float node_b;
-    cudaStream_t st, cs;            // compute stream, copy stream
-    cudaEvent_t ev[4];
+    cudaStream_t st;
     bool has_weights;
 };
 
@@ -467,8 +456,6 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
         F = hidden;
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error("session allocation failed: %s", cudaGetErrorString(e));
         nerrf_sage_session_destroy(s);
@@ -502,50 +489,14 @@ extern "C" int nerrf_sage_session_forward_host(nerrf_sage_session* s, const floa
     NERRF_REQUIRE(n_nodes >= 0 && n_nodes <= s->max_nodes && n_edges >= 0 && n_edges <= s->max_edges,
                   "graph (%lld nodes, %lld edges) exceeds the session capacity", (long long)n_nodes, (long long)n_edges);
     if (n_nodes == 0) return NERRF_OK;
-    cudaStream_t st = s->st, cs = s->cs;
-    const size_t wsb = session_ws_bytes(s->max_nodes, s->max_edges, s->hidden);
-    constexpr int NCH = 4;
-    int rc;
-    if (n_nodes >= 64 * 1024) {
-        // Pipelined: rowptr + features first, then the edge arrays in NCH row-aligned chunks on the copy stream;
-        // layer 1 of chunk c runs on the compute stream as soon as its edge block has landed, i.e. under the
-        // transfer of the following chunks.
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, cs));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, cs));
-        int64_t rcut[NCH + 1];
-        for (int c = 0; c <= NCH; ++c) rcut[c] = c == NCH ? n_nodes : ((n_nodes * c / NCH) & ~(int64_t)31);
-        for (int c = 0; c < NCH; ++c) {
-            const int64_t e0 = rowptr_host[rcut[c]], e1 = rowptr_host[rcut[c + 1]];
-            if (e1 > e0) {
-                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col + e0, col_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cs));
-                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew + e0, ew_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cs));
-            }
-            NERRF_CHECK_CUDA(cudaEventRecord(s->ev[c], cs));
-        }
-        const size_t pp = s->L > 1 ? (((size_t)n_nodes * s->hidden * sizeof(float) + 255) & ~(size_t)255) : 0;
-        void* long_ws = wsb > pp + 8192 ? (void*)((unsigned char*)s->ws + pp) : nullptr;
-        float* o0 = ((s->L - 1) % 2 == 0) ? s->h : s->ws;
-        const bool last0 = s->L == 1;
-        for (int c = 0; c < NCH; ++c) {
-            NERRF_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev[c], 0));
-            if (rcut[c + 1] == rcut[c]) continue;
-            rc = layer_fwd_impl(s->x, s->rowptr, 0, s->col, s->ew, s->Wd[0], s->bd[0], o0, n_nodes, rcut[c], rcut[c + 1], s->f_in,
-                                s->hidden, 1, algo & 0xFF, last0 ? s->node_w : nullptr, s->node_b, last0 ? s->score : nullptr,
-                                long_ws, long_ws ? wsb - pp : 0, nullptr, 0, nullptr, st);
-            if (rc) return rc;
-        }
-        rc = forward_range(o0, s->hidden, 1, s->L, s->rowptr, 0, s->col, s->ew, n_nodes, s->hidden, s->L, s->Wd, s->bd, s->node_w,
-                           s->node_b, s->h, s->score, s->ws, wsb, algo, false, st);
-        if (rc) return rc;
-    } else {
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
-        rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
-                                s->node_w, s->node_b, s->h, s->score, s->ws, wsb, algo, st);
-        if (rc) return rc;
-    }
+    cudaStream_t st = s->st;
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
+    int rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
+                                s->node_w, s->node_b, s->h, s->score, s->ws, session_ws_bytes(s->max_nodes, s->max_edges, s->hidden), algo, st);
+    if (rc) return rc;
     if (score_out_host)
         NERRF_CHECK_CUDA(cudaMemcpyAsync(score_out_host, s->score, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, st));
     if (h_out_host)
@@ -560,8 +511,6 @@ extern "C" int nerrf_sage_session_destroy(nerrf_sage_session* s) {
     cudaFree(s->score); cudaFree(s->node_w);
     for (int l = 0; l < 64; ++l) { if (s->Wd[l]) cudaFree(s->Wd[l]); if (s->bd[l]) cudaFree(s->bd[l]); }
     if (s->st) cudaStreamDestroy(s->st);
-    if (s->cs) cudaStreamDestroy(s->cs);
-    for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     delete s;
     return NERRF_OK;
 }
