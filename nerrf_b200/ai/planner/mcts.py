@@ -48,12 +48,11 @@ def ln_table(T, R) -> np.ndarray:
 def best_child(root_n, root_w) -> int:
     """argmax over children with n > 0 of (n, Q, -a): robust child, Q breaks ties, then lowest index."""
     n = np.asarray(root_n); w = np.asarray(root_w, np.float32)
-    best, bn, bq = -1, 0, np.float32(0)
-    for a in np.nonzero(n > 0)[0]:
-        q = np.float32(w[a] / np.float32(n[a]))
-        if best < 0 or n[a] > bn or (n[a] == bn and q > bq):
-            best, bn, bq = int(a), int(n[a]), q
-    return best
+    if n.size == 0 or n.max() <= 0:
+        return -1
+    top = np.nonzero(n == n.max())[0]                         # most visited
+    q = (w[top] / n[top].astype(np.float32)).astype(np.float32)
+    return int(top[np.nonzero(q == q.max())[0][0]])           # highest Q among them, lowest index on ties
 
 
 def merge_root_stats(results):
