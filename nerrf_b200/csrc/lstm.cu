@@ -60,7 +60,7 @@ lstm_layer_kernel(const float* __restrict__ in, int in_stride_b, int in_stride_t
 #pragma unroll
         for (int b = 0; b < BS; ++b) { ai[b] = bi; af[b] = bf; ag[b] = bg; ao[b] = bo; }
         // input projection
-#pragma unroll 2
+#pragma unroll 8
         for (int k = 0; k < D; ++k) {
             const float* wr = Wih + (size_t)k * 4 * LH + j;
             const float w0 = __ldg(wr), w1 = __ldg(wr + LH), w2 = __ldg(wr + 2 * LH), w3 = __ldg(wr + 3 * LH);
@@ -78,7 +78,7 @@ lstm_layer_kernel(const float* __restrict__ in, int in_stride_b, int in_stride_t
         }
         // recurrent projection
         const float* hc = h_s + cur * LH * BS;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < LH; ++k) {
             const float* wr = Whh + (size_t)k * 4 * LH + j;
             const float w0 = __ldg(wr), w1 = __ldg(wr + LH), w2 = __ldg(wr + 2 * LH), w3 = __ldg(wr + 3 * LH);
