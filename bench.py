@@ -343,7 +343,17 @@ def run_mcts_bench(dev, args, seed=0):
     t0 = time.perf_counter()
     mcts.search(act, None, R, D, seed, iterations=T, host_call=True)
     e2e_s = time.perf_counter() - t0
+    cpu = None
+    if args is None or not getattr(args, "no_cpu_baseline", False):
+        # the oracle (numpy, vectorised over the R rollouts of an iteration) on a bounded sample: 3 iterations
+        from oracle import mcts_ref
+        t0 = time.perf_counter()
+        mcts_ref.search(act.p, act.size, act.cost, R=R, D=D, T=3, seed=seed)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 3 * R / dt, "unit": "rollouts/s", "cores": 1, "kind": "port", "seconds": dt,
+               "sample": f"oracle/mcts_ref.py, 3 of the {T} iterations ({3 * R} rollouts), numpy-vectorised, single thread"}
     return {"metric": "mcts_rollouts_per_sec", "value": R * T / (ms * 1e-3), "unit": "rollouts/s", "ms_per_search": ms,
+            "cpu_baseline": cpu,
             "api_value": R * T / api_s, "e2e_value": R * T / e2e_s,
             "config": {"actions": A, "rollouts_per_iteration": R, "depth": D, "iterations": T}, "best_action": r.best,
             "note": "value: device time (CUDA events) of one search, inputs resident; api_value: SearchContext.search incl. "
