@@ -345,13 +345,15 @@ def run_mcts_bench(dev, args, seed=0):
     e2e_s = time.perf_counter() - t0
     cpu = None
     if args is None or not getattr(args, "no_cpu_baseline", False):
-        # the oracle (numpy, vectorised over the R rollouts of an iteration) on a bounded sample: 3 iterations
-        from oracle import mcts_ref
+        # the C restatement of the oracle (oracle/c/planner_oracle.c, OpenMP over the rollouts of an iteration; it is
+        # bit-identical to the numpy oracle, tests/test_oracle_c.py) on all host threads, bounded sample: 8 iterations
+        from oracle import c_oracle
+        c_oracle.search(act.p, act.size, act.cost, R=R, D=D, T=1, seed=seed)            # build + warm
         t0 = time.perf_counter()
-        mcts_ref.search(act.p, act.size, act.cost, R=R, D=D, T=3, seed=seed)
+        c_oracle.search(act.p, act.size, act.cost, R=R, D=D, T=8, seed=seed)
         dt = time.perf_counter() - t0
-        cpu = {"value": 3 * R / dt, "unit": "rollouts/s", "cores": 1, "kind": "port", "seconds": dt,
-               "sample": f"oracle/mcts_ref.py, 3 of the {T} iterations ({3 * R} rollouts), numpy-vectorised, single thread"}
+        cpu = {"value": 8 * R / dt, "unit": "rollouts/s", "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+               "sample": f"oracle/c/planner_oracle.c (OpenMP), 8 of the {T} iterations ({8 * R} rollouts)"}
     return {"metric": "mcts_rollouts_per_sec", "value": R * T / (ms * 1e-3), "unit": "rollouts/s", "ms_per_search": ms,
             "cpu_baseline": cpu,
             "api_value": R * T / api_s, "e2e_value": R * T / e2e_s,
