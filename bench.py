@@ -344,7 +344,7 @@ def run_mcts_bench(dev, args, seed=0):
     mcts.search(act, None, R, D, seed, iterations=T, host_call=True)
     e2e_s = time.perf_counter() - t0
     cpu = None
-    if args is None or not getattr(args, "no_cpu_baseline", False):
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and (args is None or not getattr(args, "no_cpu_baseline", False)):
         # the C restatement of the oracle (oracle/c/planner_oracle.c, OpenMP over the rollouts of an iteration; it is
         # bit-identical to the numpy oracle, tests/test_oracle_c.py) on all host threads, bounded sample: 8 iterations
         from oracle import c_oracle
