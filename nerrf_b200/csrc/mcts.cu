@@ -201,26 +201,27 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             if (a0 + 32 > P.A) wv |= (a0 >= P.A) ? 0xffffffffu : (0xffffffffu << (P.A - a0));
             s_state[k] = wv;
         }
-        if (tid == 0) {
-            s_node = 0; s_depth = 0; s_plen = 0; s_created = 0; s_stop = 0;
-            s_numnodes = __ldcg(P.g_num_nodes);
+        // the legal count shrinks by one per level: L(depth) = L(root) - depth, L(root) computed once per iteration
+        if (warp == 0) {
+            __syncwarp();
+            int z = 0;
+            for (int k = lane; k < NWORDS; k += 32) {
+                uint32_t wv = P.root_state ? P.root_state[k] : 0u;
+                const int a0 = k * 32;
+                if (a0 + 32 > P.A) wv |= (a0 >= P.A) ? 0xffffffffu : (0xffffffffu << (P.A - a0));
+                z += __popc(~wv);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            if (lane == 0) {
+                s_node = 0; s_depth = 0; s_plen = 0; s_created = 0;
+                s_numnodes = __ldcg(P.g_num_nodes);
+                s_L0 = z;                                                // legal actions at the root
+                s_stop = (__ldcg(P.visits) == 0 || P.D <= 0 || z == 0) ? 1 : 0;
+            }
         }
         __syncthreads();
-        while (true) {
-            // legal count (warp 0)
-            if (warp == 0) {
-                int z = 0;
-                for (int k = lane; k < NWORDS; k += 32) z += __popc(~s_state[k]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-                if (lane == 0) {
-                    s_L0 = z;
-                    const int vis = __ldcg(P.visits + s_node);
-                    if (vis == 0 || s_depth >= P.D || z == 0) s_stop = 1;
-                }
-            }
-            __syncthreads();
-            if (s_stop) break;
+        while (!s_stop) {                                                // s_stop is rewritten only between the two barriers below
             const int node = s_node;
             const float lnN = __ldg(P.lnN + __ldcg(P.visits + node));
             float best_key = -INFINITY;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                 if (ok > best_key || (ok == best_key && oa < best_a)) { best_key = ok; best_a = oa; }
             }
             if (lane == 0) { s_key[warp] = best_key; s_arg[warp] = best_a; }
-            __syncthreads();
+            __syncthreads();                                             // everyone has read s_stop / s_node / s_state
             if (tid == 0) {
                 float bk = s_key[0]; int ba = s_arg[0];
                 for (int i = 1; i < MCTS_WARPS; ++i)
@@ -254,25 +255,19 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                 s_path[s_plen] = make_int2(node, ba);
                 s_plen += 1;
                 s_state[ba >> 5] |= 1u << (ba & 31);
-                s_depth += 1;
+                const int depth_new = s_depth + 1;
+                s_depth = depth_new;
                 const int cid = __ldcg(P.child_id + base + ba);
-                if (cid < 0) { s_created = 1; s_node = s_numnodes; s_stop = 1; }
-                else s_node = cid;
+                if (cid < 0) {
+                    s_created = 1; s_node = s_numnodes; s_stop = 1;      // new leaf
+                } else {
+                    s_node = cid;                                        // descend; stop at a terminal node
+                    if (__ldcg(P.visits + cid) == 0 || depth_new >= P.D || s_L0 - depth_new == 0) s_stop = 1;
+                }
             }
             __syncthreads();
-            const int stop_now = s_stop;
-            __syncthreads();   // nobody may rewrite s_stop (loop top) before everyone has read it
-            if (stop_now) break;
         }
-        // leaf = s_node, leaf state = s_state, depth = s_depth.  (s_L0 is the legal count of the state it was
-        // computed on; recompute for the final state.)
-        if (warp == 0) {
-            int z = 0;
-            for (int k = lane; k < NWORDS; k += 32) z += __popc(~s_state[k]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-            if (lane == 0) s_L0 = z;
-        }
+        if (tid == 0) s_L0 = s_L0 - s_depth;                             // legal count of the leaf state
         __syncthreads();
         const int leaf = s_node, depth = s_depth, L0 = s_L0;
         const bool first_move = (P.D - depth) > 0 && L0 > 0;
