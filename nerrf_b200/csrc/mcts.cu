@@ -490,8 +490,7 @@ extern "C" int nerrf_mcts_search(const float* p, const float* size, const float*
     // visits, child_n, child_w, num_nodes are contiguous: zero them; child_id = -1
     NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.visits, 0, L.child_id - L.visits, st));
     NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.child_id, 0xFF, L.val - L.child_id, st));
-    const int32_t one = 1;
-    NERRF_CHECK_CUDA(cudaMemcpyAsync(ws + L.numnodes, &one, 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.numnodes, 1, 1, st));      // little-endian int32 1 (the word was zeroed above): root node
     MctsArgs a;
     a.p = p; a.size = size; a.cost = cost; a.A = A; a.root_state = root_state; a.R = R; a.D = D; a.T = T;
     a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32);
