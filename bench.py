@@ -292,6 +292,7 @@ def run_ours(args):
 
         mcts_info = run_mcts_bench(dev, args)
         lstm_info = run_lstm_bench(dev)
+        graph_info = run_graph_build_bench(dev, rp, col)
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import sage_ref as S
@@ -301,7 +302,7 @@ def run_ours(args):
         line = {"metric": "graphsage_t_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": gpu_launches, "clocks": clocks, "mcts": mcts_info, "lstm": lstm_info, "algo": args.algo}
+                "gpu_launches": gpu_launches, "clocks": clocks, "mcts": mcts_info, "lstm": lstm_info, "graph_build": graph_info, "algo": args.algo}
         print(json.dumps(line), flush=True)
         return
 
@@ -377,6 +378,32 @@ def run_lstm_bench(dev, B=4096, T=100):
     flops = B * T * 2.0 * (2 * 1024 * (16 + 256) + 2 * 1024 * (512 + 256))      # both directions, both layers
     return {"metric": "lstm_sequences_per_sec", "value": B / (ms * 1e-3), "unit": "sequences/s", "ms": ms,
             "tflops_fp32": flops / (ms * 1e-3) / 1e12, "config": {"batch": B, "T": T, "hidden": 256, "layers": 2}}
+
+
+def run_graph_build_bench(dev, rowptr, col, reps=3):
+    """Device graph constructor: the workload's own edges as a shuffled edge list -> CSR."""
+    import torch
+    from nerrf_b200.graph import build_csr_device, WINDOW
+    N, E = rowptr.numel() - 1, col.numel()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    dst = torch.repeat_interleave(torch.arange(N, device=dev, dtype=torch.int32), (rowptr[1:] - rowptr[:-1]).long())
+    perm = torch.randperm(E, generator=gen, device=dev)
+    src, dst = col[perm].contiguous(), dst[perm].contiguous()
+    t = torch.rand(E, generator=gen, device=dev) * WINDOW
+    conf = 0.5 + 0.5 * torch.rand(E, generator=gen, device=dev)
+    del perm
+    rp2, _, _ = build_csr_device(src, dst, t, conf, N)
+    assert torch.equal(rp2, rowptr), "device constructor rowptr differs"
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        build_csr_device(src, dst, t, conf, N)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = 24.0 * E + 4.0 * (N + 1)          # read src,dst,t,conf; write col,ew; write rowptr
+    return {"metric": "graph_build_edges_per_sec", "value": E / (ms * 1e-3), "unit": "edges/s", "ms": ms,
+            "algorithmic_gbps": alg / (ms * 1e-3) / 1e9, "config": {"nodes": N, "edges": E, "sort": "cub radix, 52-bit key"}}
 
 
 def main():

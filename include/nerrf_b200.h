@@ -173,6 +173,25 @@ int nerrf_lstm_forward(const float* seq, const int32_t* len, int64_t B, int T, i
                        float* out, void* workspace, size_t workspace_bytes,
                        nerrf_stream_t stream);
 
+/* ------------------------------------------------------------------ temporal-graph constructor, device half
+ * (SURVEY.md 8f rank 1 -- the step immediately before GraphSAGE_T.forward)
+ * Replaces: the graph-constructor stage the reference documents but does not ship
+ * (docs/content/docs/architecture.mdx:32-42 sliding window, inode dedup, "edge weight = causality
+ * confidence"; node schema :144-160; input records proto/trace.proto:11-49).
+ * Edge list (device, int32 src/dst in [0, n_nodes), fp32 event time t and confidence conf) ->
+ * CSR-by-destination in exactly the layout nerrf_sage_forward reads:
+ *   edges stably sorted by (dst, t);  col[i] = src;  ew[i] = conf * exp(-(t_ref - t) / tau);
+ *   rowptr[v] = #edges with dst < v   (int32, or int64 when rowptr_is64; n_edges >= 2^31 needs int64).
+ * rowptr and col are bit-exact against the host constructor (nerrf_b200/graph.py csr_from_edges);
+ * ew differs only by the exp implementation (<= 2 ulp).  Deterministic (no atomics).
+ * Limits: n_edges < 2^32, n_nodes < 2^31.  workspace: nerrf_graph_csr_workspace_bytes, 256-byte
+ * aligned.  The call waits for `stream` once, to report out-of-range vertex ids as NERRF_ERR_INVALID. */
+int nerrf_graph_csr_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t* bytes);
+int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, const float* t, const float* conf,
+                          int64_t n_edges, int64_t n_nodes, float t_ref, float tau,
+                          void* rowptr_out, int rowptr_is64, int32_t* col_out, float* ew_out,
+                          void* workspace, int64_t workspace_bytes, nerrf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

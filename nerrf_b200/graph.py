@@ -57,6 +57,38 @@ def csr_from_edges(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU):
     return rowptr, src.astype(np.int32), ew
 
 
+def build_csr_device(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU, rowptr_dtype=None):
+    """Device half of the graph constructor (include/nerrf_b200.h nerrf_graph_build_csr): CUDA int32 src/dst and
+    fp32 t/conf tensors -> (rowptr, col, ew) CUDA tensors, same contract as csr_from_edges (rowptr/col bit-exact,
+    ew within the exp implementation's 2 ulp).  No CPU fallback."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    _lib.require_cuda(src, dst, t, conf)
+    E = int(src.shape[0])
+    if not (dst.shape[0] == t.shape[0] == conf.shape[0] == E):
+        raise ValueError("src, dst, t, conf must have the same length")
+    if src.dtype != torch.int32 or dst.dtype != torch.int32 or t.dtype != torch.float32 or conf.dtype != torch.float32:
+        raise TypeError("build_csr_device takes int32 src/dst and float32 t/conf")
+    src, dst, t, conf = src.contiguous(), dst.contiguous(), t.contiguous(), conf.contiguous()
+    dev = src.device
+    if rowptr_dtype is None:
+        rowptr_dtype = torch.int64 if E >= 2 ** 31 else torch.int32
+    h = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = C.c_int64()
+        _lib.check(h.nerrf_graph_csr_workspace_bytes(E, int(N), C.byref(nbytes)), "nerrf_graph_csr_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(int(N) + 1, dtype=rowptr_dtype, device=dev)
+        col = torch.empty(E, dtype=torch.int32, device=dev)
+        ew = torch.empty(E, dtype=torch.float32, device=dev)
+        _lib.check(h.nerrf_graph_build_csr(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(t), _lib.ptr(conf), E, int(N),
+                                           float(t_ref), float(tau), _lib.ptr(rowptr), int(rowptr_dtype == torch.int64),
+                                           _lib.ptr(col), _lib.ptr(ew), _lib.ptr(ws), ws.numel(),
+                                           _lib.current_stream_ptr()), "nerrf_graph_build_csr")
+    return rowptr, col, ew
+
+
 def synthetic_graph(N=1_000_000, E=10_000_000, seed=20250115, hub="src", feat_seed=0, f_in=F_IN) -> TemporalGraph:
     """SURVEY.md 8d cfg 2/4 generator: dst ~ U{0..N-1}, src = floor(N*u^3) (hub sources, one
     ransomware pid touching many files); hub="dst" swaps the roles (long rows)."""

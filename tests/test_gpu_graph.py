@@ -1,0 +1,119 @@
+"""GPU parity: device graph constructor (nerrf_graph_build_csr) vs the host constructor graph.csr_from_edges.
+rowptr / col are index work: bit-exact.  ew = conf * exp(.): fp32, |err| <= 6 ulp of the host value (numpy's and
+CUDA's expf are both faithfully rounded to within 1-2 ulp, not correctly rounded)."""
+import numpy as np
+import pytest
+import torch
+
+from nerrf_b200 import graph as G
+from nerrf_b200._lib import NerrfError
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_csr(src, dst, t, conf, N, **kw):
+    c = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).cuda()
+    rp, col, ew = G.build_csr_device(c(src, np.int32), c(dst, np.int32), c(t, np.float32), c(conf, np.float32), N, **kw)
+    return rp.cpu().numpy(), col.cpu().numpy(), ew.cpu().numpy()
+
+
+def _check(src, dst, t, conf, N, **kw):
+    t = t.astype(np.float32); conf = conf.astype(np.float32)
+    rp_w, col_w, ew_w = G.csr_from_edges(src.astype(np.int64), dst.astype(np.int64), t, conf, N, **kw)
+    rp, col, ew = _device_csr(src, dst, t, conf, N, **kw)
+    assert rp.dtype == rp_w.dtype
+    assert np.array_equal(rp, rp_w)
+    assert np.array_equal(col, col_w)
+    assert np.all(np.abs(ew - ew_w) <= 6 * np.spacing(np.abs(ew_w)))
+    return rp, col, ew
+
+
+@pytest.mark.parametrize("N,E,seed", [(1, 5, 0), (7, 0, 1), (50, 400, 2), (1000, 20_000, 3), (100_000, 1_000_000, 4)])
+def test_random_edge_lists(N, E, seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, N, E); dst = rng.integers(0, N, E)
+    t = rng.uniform(0, 60, E); conf = rng.uniform(0.5, 1.0, E)
+    if E == 0:
+        rp, col, ew = _device_csr(src, dst, t, conf, N)
+        assert np.array_equal(rp, np.zeros(N + 1, np.int32)) and col.size == 0 and ew.size == 0
+    else:
+        _check(src, dst, t, conf, N)
+
+
+def test_ties_keep_input_order_and_signed_zero_times():
+    # many equal (dst, t) pairs: the stable order is the input order; -0.0 and +0.0 are the same time
+    rng = np.random.default_rng(5)
+    E, N = 5000, 40
+    src = rng.integers(0, N, E); dst = rng.integers(0, 8, E)
+    t = rng.integers(-2, 3, E).astype(np.float32) * np.float32(0.5)
+    t[rng.random(E) < 0.1] = np.float32(-0.0)
+    _check(src, dst, t, np.ones(E), N, t_ref=1.0)
+
+
+def test_sparse_destinations_long_empty_runs():
+    # edges land on a handful of far-apart rows: long empty-row gaps before, between and after
+    N = 300_000
+    dst = np.repeat(np.array([17, 18, 120_000, 299_000]), 300)
+    rng = np.random.default_rng(6)
+    src = rng.integers(0, N, dst.size); t = rng.uniform(0, 60, dst.size)
+    rp, _, _ = _check(src, dst, t, np.ones(dst.size), N)
+    assert rp[0] == 0 and rp[17] == 0 and rp[18] == 300 and rp[-1] == dst.size
+
+
+def test_hub_destination_and_cfg2_shape_roundtrip_through_forward():
+    # constructor output feeds GraphSAGE_T.forward directly; the result equals the forward on the host-built CSR
+    from nerrf_b200.ai.models import GraphSAGE_T
+    g_src = G.synthetic_graph(N=20_000, E=200_000, seed=7, hub="dst")
+    rows = np.repeat(np.arange(g_src.num_nodes), np.diff(g_src.rowptr))
+    rng = np.random.default_rng(8)
+    shuffle = rng.permutation(rows.size)                      # undo the sort: a raw, unordered edge list
+    src = g_src.col[shuffle]; dst = rows[shuffle]
+    t = rng.uniform(0, 60, rows.size).astype(np.float32); conf = rng.uniform(0.5, 1, rows.size).astype(np.float32)
+    rp_w, col_w, ew_w = G.csr_from_edges(src.astype(np.int64), dst.astype(np.int64), t, conf, g_src.num_nodes)
+    c = lambda a: torch.from_numpy(a).cuda()
+    rp, col, ew = G.build_csr_device(c(src.astype(np.int32)), c(dst.astype(np.int32)), c(t), c(conf), g_src.num_nodes)
+    assert torch.equal(rp.cpu(), torch.from_numpy(rp_w)) and torch.equal(col.cpu(), torch.from_numpy(col_w))
+    model = GraphSAGE_T(32, 128, 3).cuda()
+    x = c(g_src.x)
+    h_dev, s_dev = model(x, rp, col, ew)
+    h_host, s_host = model(x, c(rp_w), c(col_w), c(ew_w))
+    rms = float(h_host.pow(2).mean().sqrt())
+    assert float((h_dev - h_host).abs().max()) <= 1e-5 * rms      # only the <=2-ulp weight difference separates them
+    assert float((s_dev - s_host).abs().max()) <= 1e-5
+
+
+def test_int64_rowptr_variant():
+    rng = np.random.default_rng(9)
+    N, E = 500, 9000
+    src = rng.integers(0, N, E).astype(np.int32); dst = rng.integers(0, N, E).astype(np.int32)
+    t = rng.uniform(0, 60, E).astype(np.float32); conf = np.ones(E, np.float32)
+    c = lambda a: torch.from_numpy(a).cuda()
+    rp64, col64, _ = G.build_csr_device(c(src), c(dst), c(t), c(conf), N, rowptr_dtype=torch.int64)
+    rp32, col32, _ = G.build_csr_device(c(src), c(dst), c(t), c(conf), N)
+    assert rp64.dtype == torch.int64 and torch.equal(rp64, rp32.long()) and torch.equal(col64, col32)
+
+
+def test_out_of_range_vertex_is_an_error_not_a_crash():
+    c = lambda a: torch.from_numpy(a).cuda()
+    src = np.array([0, 1, 2], np.int32); t = np.zeros(3, np.float32); conf = np.ones(3, np.float32)
+    for bad_dst in (np.array([0, 9, 1], np.int32), np.array([0, -1, 1], np.int32)):
+        with pytest.raises(NerrfError, match="outside"):
+            G.build_csr_device(c(src), c(bad_dst), c(t), c(conf), 3)
+    with pytest.raises(NerrfError, match="outside"):
+        G.build_csr_device(c(np.array([0, 7, 2], np.int32)), c(np.array([0, 1, 2], np.int32)), c(t), c(conf), 3)
+    rp, col, _ = G.build_csr_device(c(src), c(np.array([2, 0, 2], np.int32)), c(t), c(conf), 3)    # still usable after
+    assert rp.tolist() == [0, 1, 1, 3] and col.tolist() == [1, 0, 2]
+
+
+@pytest.mark.parametrize("name", ["m0", "m1"])
+def test_reference_trace_graphs_rebuild_from_shuffled_edges(name):
+    # golden CSR of the reference's m0 / m1 traces (tests/golden/make_golden.py) -> shuffled edge list -> device
+    # constructor gives the golden CSR back.  time = slot inside the golden CSR, so the (dst, t) order is the golden order.
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_m1_graph.npz"))
+    rowptr, col, ew = z[name + "_rowptr"], z[name + "_col"], z[name + "_ew"]
+    rows = np.repeat(np.arange(rowptr.size - 1), np.diff(rowptr))
+    order = np.random.default_rng(10).permutation(col.size)
+    slot = np.arange(col.size, dtype=np.float32)
+    rp, c2, w2 = _device_csr(col[order], rows[order], slot[order], ew[order], rowptr.size - 1, t_ref=0.0, tau=1e30)
+    assert np.array_equal(rp, rowptr) and np.array_equal(c2, col) and np.array_equal(w2, ew)   # exp(~0) == 1 exactly
