@@ -1,1 +1,1 @@
-from nerrf_b200.ai.planner import mcts, rewards  # noqa: F401
+from nerrf_b200.ai.planner import emit, mcts, rewards  # noqa: F401

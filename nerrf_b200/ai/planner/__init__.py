@@ -1,1 +1,1 @@
-from . import mcts, rewards  # noqa: F401
+from . import emit, mcts, rewards  # noqa: F401

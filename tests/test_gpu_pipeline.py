@@ -24,6 +24,12 @@ def test_pipeline_reverts_exactly_the_encrypted_files():
     assert sorted(res.plan_nodes) == sorted(np.nonzero(label)[0].tolist())
     assert res.probs.shape == (len(nodes), 2) and torch.isfinite(res.node_score).all()
     assert set(res.timings_ms) >= {"h2d_graph", "graphsage_t", "lstm", "mcts_plan", "total"}
+    # the emitted undo plan renames every encrypted twin back (m1_rollback.sh semantics), in plan order
+    from nerrf_b200.ai.planner import emit
+    up = emit.from_pipeline(g, res, attack_id="sim-7")
+    assert [s["node"] for s in up["steps"]] == res.plan_nodes
+    assert all(s["op"] == "rename" and s["from"].endswith(".lockbit3") and s["to"].endswith(".dat") for s in up["steps"])
+    assert up["reward_after"] > up["reward_before"]
     # model-driven confidence path runs too (random weights: only structural checks)
     res2 = pipeline.run(g, seq, lengths, nodes, model, seq_model, top_a=32, n_rollouts=256, depth=10, iterations=4, plan_steps=3)
     assert len(res2.candidates) == 32 and len(res2.plan_nodes) <= 3
