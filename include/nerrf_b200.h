@@ -192,6 +192,40 @@ int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, const float* t
                           void* rowptr_out, int rowptr_is64, int32_t* col_out, float* ew_out,
                           void* workspace, int64_t workspace_bytes, nerrf_stream_t stream);
 
+/* ------------------------------------------------------------------ EventBatch ingest (HOST code)
+ * (SURVEY.md 8f rank 2 -- the wire format on the input side of the path)
+ * Replaces: the consumer of the tracker's gRPC stream (proto/trace.proto:11-49 Event, :47-49
+ * EventBatch; producer tracker/cmd/tracker/main.go:229-252).  `buf` holds one serialized
+ * nerrf.trace.EventBatch, or any number of them concatenated (repeated fields append).
+ * nerrf_trace_scan counts the events (top-level hop) and gives an upper bound per string column
+ * (string_bytes[4] = comm, syscall, path, new_path; exact totals are off[n_events] after decoding);
+ * nerrf_trace_decode parses the events once and fills caller-owned arrays: scalars [n_events]; strings as offsets [n_events+1]
+ * + packed bytes; event_slot = graph feature slot of the syscall name (0 file_created,
+ * 1 file_encrypt_start, 2 file_encrypt_complete, 3 ransom_note_created, 4 openat, 5 write,
+ * 6 rename, 7 other); path_flags = NERRF_PATH_* bits of `path`.  Malformed input ->
+ * NERRF_ERR_INVALID with the byte offset in nerrf_last_error().
+ * nerrf_trace_intern: pid / path interning ("merge by inode", architecture.mdx:41): node ids in
+ * order of first appearance over events visited in `order` (NULL = as stored); node tables sized
+ * by the caller (node_capacity >= 2*n_events with merge_renames, 3*n_events without);
+ * node_name_which: 0 = path, 1 = new_path of event node_name_event, 2 = the pid itself. */
+#define NERRF_PATH_LOCKBIT   1   /* ".lockbit" in path */
+#define NERRF_PATH_NOTE      2   /* README / RANSOM (ASCII case-insensitive) in path */
+#define NERRF_PATH_TMP       4   /* path starts with /tmp or /proc */
+#define NERRF_PATH_ENCRYPTED 8   /* path ends with ".lockbit3" (benchmarks/m1/scripts/m1_rollback.sh:95) */
+int nerrf_trace_scan(const uint8_t* buf, int64_t len, int64_t* n_events, int64_t* string_bytes);
+int nerrf_trace_decode(const uint8_t* buf, int64_t len, int64_t n_events,
+                       int64_t* ts_sec, int32_t* ts_nanos, uint32_t* pid, uint32_t* tid,
+                       int32_t* flags, int64_t* ret_val, uint64_t* bytes,
+                       uint8_t* event_slot, uint8_t* path_flags,
+                       int64_t* comm_off, uint8_t* comm_data, int64_t* syscall_off, uint8_t* syscall_data,
+                       int64_t* path_off, uint8_t* path_data, int64_t* new_path_off, uint8_t* new_path_data);
+int nerrf_trace_intern(int64_t n_events, const int64_t* order, const uint32_t* pid,
+                       const int64_t* path_off, const uint8_t* path_data,
+                       const int64_t* new_path_off, const uint8_t* new_path_data, int merge_renames,
+                       int32_t* node_p, int32_t* node_f, int32_t* node_g, int64_t* n_nodes,
+                       int8_t* node_kind, int64_t* node_name_event, int8_t* node_name_which,
+                       int64_t node_capacity);
+
 #ifdef __cplusplus
 }
 #endif

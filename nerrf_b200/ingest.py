@@ -1,0 +1,231 @@
+"""EventBatch ingest and the columnar graph constructor (host side).
+
+    wire bytes of nerrf.trace.EventBatch  --decode_event_batch-->  EventColumns (numpy, columnar)
+    EventColumns  --graph_from_columns-->  TemporalGraph        (same graph as graph.graph_from_events, no per-event
+                                                                  Python: interning in C++, everything else vectorised;
+                                                                  device=... runs the sort/CSR stage on the GPU)
+
+Reference anchors: proto/trace.proto:11-49 (Event), :47-49 (EventBatch), producer
+tracker/cmd/tracker/main.go:229-252; constructor prose docs/content/docs/architecture.mdx:32-42,144-160.
+The decoder and the interning live in the C-ABI library (csrc/ingest.cu: nerrf_trace_scan / _decode / _intern).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from . import graph as G
+
+STRING_COLUMNS = ("comm", "syscall", "path", "new_path")
+
+
+@dataclass
+class EventColumns:
+    n: int
+    ts_sec: np.ndarray        # int64  [n]   google.protobuf.Timestamp.seconds
+    ts_nanos: np.ndarray      # int32  [n]
+    pid: np.ndarray           # uint32 [n]
+    tid: np.ndarray           # uint32 [n]
+    flags: np.ndarray         # int32  [n]   Event.OpenFlags
+    ret_val: np.ndarray       # int64  [n]
+    bytes: np.ndarray         # uint64 [n]
+    event_slot: np.ndarray    # uint8  [n]   feature slot of the syscall / event name (graph._EVENT_SLOT, 7 = other)
+    path_flags: np.ndarray    # uint8  [n]   NERRF_PATH_* bits
+    strings: dict             # name -> (offsets int64 [n+1], data uint8 [bytes])
+
+    def text(self, column: str, i: int) -> str:
+        off, data = self.strings[column]
+        return bytes(data[off[i]:off[i + 1]]).decode("utf-8", "replace")
+
+    def texts(self, column: str) -> list:
+        off, data = self.strings[column]
+        raw = data.tobytes()
+        return [raw[off[i]:off[i + 1]].decode("utf-8", "replace") for i in range(self.n)]
+
+    @property
+    def timestamp(self) -> np.ndarray:
+        """seconds as float64, the same arithmetic as graph.events_from_event_batch (seconds + nanos * 1e-9)."""
+        return self.ts_sec.astype(np.float64) + self.ts_nanos.astype(np.float64) * 1e-9
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def decode_event_batch(buf) -> EventColumns:
+    """buf: bytes / bytearray / memoryview / uint8 array holding one serialized EventBatch (or several concatenated)."""
+    raw = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, np.uint8)
+    h = _lib.lib()
+    n = C.c_int64()
+    sb = (C.c_int64 * 4)()
+    _lib.check(h.nerrf_trace_scan(_p(raw) if raw.size else None, raw.size, C.byref(n), sb), "nerrf_trace_scan")
+    n = n.value
+    cols = dict(ts_sec=np.empty(n, np.int64), ts_nanos=np.empty(n, np.int32), pid=np.empty(n, np.uint32),
+                tid=np.empty(n, np.uint32), flags=np.empty(n, np.int32), ret_val=np.empty(n, np.int64),
+                bytes=np.empty(n, np.uint64), event_slot=np.empty(n, np.uint8), path_flags=np.empty(n, np.uint8))
+    strings = {name: (np.zeros(n + 1, np.int64), np.empty(max(int(sb[k]), 1), np.uint8)) for k, name in enumerate(STRING_COLUMNS)}   # upper bounds
+    args = [_p(cols[k]) for k in ("ts_sec", "ts_nanos", "pid", "tid", "flags", "ret_val", "bytes", "event_slot", "path_flags")]
+    for name in STRING_COLUMNS:
+        args += [_p(strings[name][0]), _p(strings[name][1])]
+    _lib.check(h.nerrf_trace_decode(_p(raw) if raw.size else None, raw.size, n, *args), "nerrf_trace_decode")
+    strings = {name: (off, data[:off[-1]].copy()) for name, (off, data) in strings.items()}
+    return EventColumns(n=n, strings=strings, **cols)
+
+
+def events_from_columns(cols: EventColumns) -> list:
+    """The dict schema of graph.events_from_event_batch / the JSONL traces (for the per-event host loader)."""
+    ts = cols.timestamp
+    sys_, path, new_path = cols.texts("syscall"), cols.texts("path"), cols.texts("new_path")
+    return [{"timestamp": float(ts[i]), "event": sys_[i], "path": path[i], "size": int(cols.bytes[i]),
+             "pid": int(cols.pid[i]), "new_path": new_path[i]} for i in range(cols.n)]
+
+
+def intern_nodes(cols: EventColumns, order=None, merge_renames=True):
+    """-> node_p, node_f, node_g (int32 [n], by stored event index; node_g = -1 when absent), kind int8 [N],
+    name_event int64 [N], name_which int8 [N]."""
+    n = cols.n
+    cap = max((2 if merge_renames else 3) * n, 1)
+    node_p = np.zeros(n, np.int32); node_f = np.zeros(n, np.int32); node_g = np.zeros(n, np.int32)
+    kind = np.zeros(cap, np.int8); name_event = np.zeros(cap, np.int64); name_which = np.zeros(cap, np.int8)
+    nn = C.c_int64()
+    order_p = None
+    if order is not None:
+        order = np.ascontiguousarray(order, np.int64)
+        order_p = _p(order)
+    (poff, pdata), (goff, gdata) = cols.strings["path"], cols.strings["new_path"]
+    pdata = pdata if pdata.size else np.zeros(1, np.uint8)
+    gdata = gdata if gdata.size else np.zeros(1, np.uint8)
+    _lib.check(_lib.lib().nerrf_trace_intern(n, order_p, _p(cols.pid), _p(poff), _p(pdata), _p(goff), _p(gdata),
+                                             int(bool(merge_renames)), _p(node_p), _p(node_f), _p(node_g), C.byref(nn),
+                                             _p(kind), _p(name_event), _p(name_which), cap), "nerrf_trace_intern")
+    N = nn.value
+    return node_p, node_f, node_g, kind[:N].copy(), name_event[:N].copy(), name_which[:N].copy()
+
+
+def _node_names(cols, name_event, name_which):
+    """pid nodes -> "pid:<pid>"; file nodes -> the path (or new_path) of the event that names them."""
+    (poff, pdata), (goff, gdata) = cols.strings["path"], cols.strings["new_path"]
+    praw, graw = pdata.tobytes(), gdata.tobytes()
+    pa, pb = poff[name_event].tolist(), poff[name_event + 1].tolist()
+    ga, gb = goff[name_event].tolist(), goff[name_event + 1].tolist()
+    pids = cols.pid[name_event].tolist()
+    return ["pid:%d" % pids[v] if w == 2 else (praw[pa[v]:pb[v]] if w == 0 else graw[ga[v]:gb[v]]).decode("utf-8", "replace")
+            for v, w in enumerate(name_which.tolist())]
+
+
+def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, device=None) -> G.TemporalGraph:
+    """Same graph as graph.graph_from_events(events_from_columns(cols)) -- nodes, numbering, CSR, weights, features,
+    labels -- without a per-event Python loop.  device=None: arrays are numpy (host CSR stage).  device="cuda[:i]":
+    the edge sort / CSR / temporal weights run on the GPU (graph.build_csr_device) and rowptr, col, ew, x are CUDA
+    tensors ready for GraphSAGE_T.forward."""
+    n = cols.n
+    if n == 0:
+        raise ValueError("empty trace")
+    ts = cols.timestamp
+    order = np.argsort(ts, kind="stable")                     # lossy streams may be unordered (main.go:257-263)
+    t0 = float(ts[order[0]]); t1 = float(ts[order[-1]])
+    span = max(t1 - t0, 1e-6)
+    window = window or max(span, G.WINDOW)
+    node_p, node_f, node_g, kind, name_event, name_which = intern_nodes(cols, order, merge_renames)
+    N = kind.shape[0]
+    P = node_p[order].astype(np.int64); F = node_f[order].astype(np.int64); Gn = node_g[order].astype(np.int64)
+    t = ts[order] - t0
+    slot = cols.event_slot[order].astype(np.int64)
+    size = cols.bytes[order].astype(np.float64)
+    pf = cols.path_flags[order]
+    has_g = Gn >= 0
+
+    # edges, in the per-event order of the host loader: p->f, f->p [, f->g, g->f]
+    src4 = np.stack([P, F, F, Gn], 1); dst4 = np.stack([F, P, Gn, F], 1)
+    keep = np.stack([np.ones(n, bool), np.ones(n, bool), has_g, has_g], 1).ravel()
+    src = src4.ravel()[keep]; dst = dst4.ravel()[keep]
+    tt = np.repeat(t, 4)[keep].astype(np.float32)
+    conf = np.ones(src.shape[0], np.float32)
+
+    # per-node features over the touched nodes (p, f [, g]) of every event
+    tn = np.concatenate([P, F, Gn[has_g]]); tslot = np.concatenate([slot, slot, slot[has_g]])
+    tsize = np.concatenate([size, size, size[has_g]]); ttime = np.concatenate([t, t, t[has_g]])
+    cnt = np.bincount(tn * G._N_EVENT_SLOTS + tslot, minlength=N * G._N_EVENT_SLOTS).reshape(N, G._N_EVENT_SLOTS).astype(np.float64)
+    nbytes = np.bincount(tn, weights=tsize, minlength=N)
+    first = np.full(N, np.inf); last = np.full(N, -np.inf)
+    np.minimum.at(first, tn, ttime); np.maximum.at(last, tn, ttime)
+    flag = lambda bit: (np.bincount(F[(pf & bit) != 0], minlength=N) > 0).astype(np.float64)
+    lockbit, note, tmp = flag(1), flag(2), flag(4)
+    label = (np.bincount(F[(slot == 1) | (slot == 2)], minlength=N) > 0).astype(np.int64)
+
+    indeg = np.bincount(dst, minlength=N).astype(np.float32)
+    outdeg = np.bincount(src, minlength=N).astype(np.float32)
+    x = np.zeros((N, G.F_IN), np.float32)
+    x[:, 0] = kind == 0; x[:, 1] = kind == 1
+    x[:, 3] = np.log1p(indeg.astype(np.float64)); x[:, 4] = np.log1p(outdeg.astype(np.float64))
+    x[:, 5:5 + G._N_EVENT_SLOTS] = np.log1p(cnt)
+    x[:, 13] = np.log1p(nbytes) / 20.0
+    x[:, 14] = (last - first) / window
+    x[:, 15] = first / window
+    x[:, 16] = lockbit; x[:, 17] = note; x[:, 18] = tmp
+    wr = cnt[:, 1] + cnt[:, 5]
+    x[:, 19] = np.divide(cnt[:, 2], wr, out=np.zeros(N), where=wr > 0)
+    k = np.maximum(cnt[:, 0] + cnt[:, 1] + cnt[:, 2], 1.0)
+    size_mb = np.where(kind == 0, nbytes / k / 1e6, 0.0).astype(np.float32)
+
+    names = _node_names(cols, name_event, name_which)
+    meta = {"kind": "trace", "names": names, "node_kind": kind.astype(np.int64), "label": label, "size_mb": size_mb,
+            "t0": t0, "span": span}
+    if device is None:
+        rowptr, col, ew = G.csr_from_edges(src, dst, tt, conf, N, t_ref=float(span), tau=G.TAU)
+        return G.TemporalGraph(rowptr, col, ew, x, meta)
+    import torch
+    dev = torch.device(device)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev)
+    rowptr, col, ew = G.build_csr_device(up(src, np.int32), up(dst, np.int32), up(tt, np.float32), up(conf, np.float32), N,
+                                         t_ref=float(span), tau=G.TAU)
+    meta["device"] = str(dev)
+    return G.TemporalGraph(rowptr, col, ew, torch.from_numpy(x).to(dev), meta)
+
+
+# ------------------------------------------------------------------ test / tooling helper (not on the product path)
+def encode_event_batch(events) -> bytes:
+    """Minimal protobuf WRITER for nerrf.trace.EventBatch (proto3 canonical form: default-valued fields omitted),
+    so traces in the dict schema can be replayed through the ingest path without protoc.  events: dicts with
+    ts=(seconds, nanos) | None or timestamp=float seconds, pid, tid, comm, syscall|event, path, new_path, flags, ret_val,
+    bytes|size."""
+    def varint(v):
+        v &= (1 << 64) - 1
+        out = bytearray()
+        while True:
+            b = v & 0x7f
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+
+    def field_varint(num, v):
+        return b"" if v == 0 else varint(num << 3) + varint(v)
+
+    def field_bytes(num, s, keep_empty=False):
+        s = s.encode("utf-8") if isinstance(s, str) else bytes(s)
+        return b"" if (not s and not keep_empty) else varint(num << 3 | 2) + varint(len(s)) + s
+
+    out = bytearray()
+    for e in events:
+        if "ts" in e and e["ts"] is None:
+            sec = nanos = None                       # field absent (presence matters for sub-messages)
+        elif "ts" in e:
+            sec, nanos = e["ts"]
+        else:
+            tsf = float(e["timestamp"]) if not isinstance(e["timestamp"], str) else G._parse_ts(e["timestamp"])
+            sec = int(np.floor(tsf)); nanos = int(round((tsf - sec) * 1e9))
+            if nanos >= 1_000_000_000:
+                sec += 1; nanos -= 1_000_000_000
+        ts = b"" if sec is None else field_bytes(1, field_varint(1, sec) + field_varint(2, nanos), keep_empty=True)
+        rv = int(e.get("ret_val", 0))
+        body = (ts + field_varint(2, int(e.get("pid", 0))) + field_varint(3, int(e.get("tid", 0)))
+                + field_bytes(4, e.get("comm", "")) + field_bytes(5, e.get("syscall", e.get("event", "")))
+                + field_bytes(6, e.get("path", "")) + field_bytes(7, e.get("new_path", "") or "")
+                + field_varint(8, int(e.get("flags", 0))) + field_varint(9, (rv << 1) ^ (rv >> 63))
+                + field_varint(10, int(e.get("bytes", e.get("size", 0)) or 0)))
+        out += varint(1 << 3 | 2) + varint(len(body)) + body
+    return bytes(out)

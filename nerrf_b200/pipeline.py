@@ -78,7 +78,9 @@ def run(g: G.TemporalGraph, seq, lengths, seq_nodes, model: GraphSAGE_T, seq_mod
     sync = torch.cuda.synchronize
 
     t0 = time.perf_counter()
-    x, rp, col, ew = (torch.from_numpy(a).to(dev, non_blocking=True) for a in (g.x, g.rowptr, g.col, g.ew))
+    # numpy arrays (host constructor) are uploaded; CUDA tensors (ingest.graph_from_columns(device=...)) are used as is
+    x, rp, col, ew = ((a if torch.is_tensor(a) else torch.from_numpy(a)).to(dev, non_blocking=True)
+                      for a in (g.x, g.rowptr, g.col, g.ew))
     sync(); tm["h2d_graph"] = (time.perf_counter() - t0) * 1e3
 
     t0 = time.perf_counter()

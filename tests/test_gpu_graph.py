@@ -117,3 +117,24 @@ def test_reference_trace_graphs_rebuild_from_shuffled_edges(name):
     slot = np.arange(col.size, dtype=np.float32)
     rp, c2, w2 = _device_csr(col[order], rows[order], slot[order], ew[order], rowptr.size - 1, t_ref=0.0, tau=1e30)
     assert np.array_equal(rp, rowptr) and np.array_equal(c2, col) and np.array_equal(w2, ew)   # exp(~0) == 1 exactly
+
+
+def test_wire_bytes_to_device_graph_to_plan():
+    # EventBatch wire bytes -> columns -> graph with the CSR stage on the GPU -> the same graph as the host path,
+    # and the pipeline runs on the device-resident graph without another upload
+    from nerrf_b200 import ingest, pipeline, trace_sim
+    from nerrf_b200.ai.models import GraphSAGE_T, lstm
+    ev = trace_sim.lockbit_trace(n_files=20, seed=11, benign_files=15)
+    cols = ingest.decode_event_batch(ingest.encode_event_batch(ev))
+    host = ingest.graph_from_columns(cols)
+    dev = ingest.graph_from_columns(cols, device="cuda")
+    assert dev.rowptr.is_cuda and dev.x.is_cuda and dev.num_nodes == host.num_nodes
+    assert np.array_equal(dev.rowptr.cpu().numpy(), host.rowptr) and np.array_equal(dev.col.cpu().numpy(), host.col)
+    assert np.all(np.abs(dev.ew.cpu().numpy() - host.ew) <= 6 * np.spacing(np.abs(host.ew)))
+    assert np.array_equal(dev.x.cpu().numpy(), host.x)
+    seq, lengths, nodes = pipeline.file_sequences(ingest.events_from_columns(cols), host)
+    label = host.meta["label"].astype(bool)
+    model = GraphSAGE_T(32, 128, 2).cuda(); seq_model = lstm.LSTMScorer().cuda()
+    res = pipeline.run(dev, seq, lengths, nodes, model, seq_model, top_a=4096, confidence=np.where(label, 0.95, 0.05),
+                       n_rollouts=512, depth=30, iterations=6)
+    assert sorted(res.plan_nodes) == sorted(np.nonzero(label)[0].tolist())
