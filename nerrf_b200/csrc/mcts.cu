@@ -175,7 +175,7 @@ struct MctsArgs {
 
 template <int NW>
 __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
-    constexpr int CHUNK = 32 * NW, A_PAD = 1024 * NW, NWORDS = 32 * NW;
+    constexpr int A_PAD = 1024 * NW, NWORDS = 32 * NW;
     unsigned bar_target = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* u_s = reinterpret_cast<float*>(smem_raw);
