@@ -192,6 +192,24 @@ int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, const float* t
                           void* rowptr_out, int rowptr_is64, int32_t* col_out, float* ew_out,
                           void* workspace, int64_t workspace_bytes, nerrf_stream_t stream);
 
+/* Per-node features on the device (rest of SURVEY.md 8f rank 1): event columns already mapped to node
+ * ids (nerrf_trace_intern, events in time order) -> x [n_nodes, 32] in the layout GraphSAGE_T.forward
+ * reads (node schema docs/content/docs/architecture.mdx:144-160, threat-model.mdx:154-184; column
+ * meaning nerrf_b200/graph.py graph_from_events): 0 file, 1 process, 3/4 log1p(in/out degree),
+ * 5..12 log1p(event-kind counts), 13 log1p(bytes)/20, 14 (last-first)/window, 15 first/window,
+ * 16 .lockbit, 17 ransom-note, 18 /tmp|/proc, 19 completes/(starts+writes); label_out (0/1: the file
+ * was encrypted) and size_mb_out are optional.  Device pointers; t = seconds since the first event
+ * (>= 0, double); node_g may be NULL (no rename targets).  Integer atomics only -> deterministic;
+ * equals the host constructor up to the rounding of log1p (<= 1 ulp of fp32).  Waits for `stream`
+ * once to report malformed columns. */
+int nerrf_graph_node_features_workspace_bytes(int64_t n_nodes, int64_t* bytes);
+int nerrf_graph_node_features(const int32_t* node_p, const int32_t* node_f, const int32_t* node_g,
+                              const double* t, const uint8_t* event_slot, const uint64_t* bytes,
+                              const uint8_t* path_flags, int64_t n_events, const int8_t* node_kind,
+                              int64_t n_nodes, double window, float* x_out, int32_t* label_out,
+                              float* size_mb_out, void* workspace, int64_t workspace_bytes,
+                              nerrf_stream_t stream);
+
 /* ------------------------------------------------------------------ EventBatch ingest (HOST code)
  * (SURVEY.md 8f rank 2 -- the wire format on the input side of the path)
  * Replaces: the consumer of the tracker's gRPC stream (proto/trace.proto:11-49 Event, :47-49

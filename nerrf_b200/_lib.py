@@ -52,6 +52,9 @@ SIGNATURES = {
     "nerrf_graph_csr_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "nerrf_graph_build_csr": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, vp, C.c_int,
                                         vp, vp, vp, C.c_int64, vp]),
+    "nerrf_graph_node_features_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
+    "nerrf_graph_node_features": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, vp, vp, vp,
+                                            vp, C.c_int64, vp]),
     "nerrf_trace_scan": (C.c_int, [vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nerrf_trace_decode": (C.c_int, [vp, C.c_int64, C.c_int64] + [vp] * 17),
     "nerrf_trace_intern": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64),

@@ -83,6 +83,101 @@ __global__ void csr_empty_kernel(RP* rowptr, int64_t N) {
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v <= N; v += stride) rowptr[v] = 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-node features ("feature counts"): spec = nerrf_b200/ingest.py graph_from_columns /
+// graph.py graph_from_events (node schema: docs/content/docs/architecture.mdx:144-160, threat-model.mdx:154-184).
+// Pass 1 over events: integer atomics only (event-kind counts, byte sums, first/last touch time as ordered int64,
+// path flag bits, degree) -> deterministic.  Pass 2 over nodes: the 20 used feature columns in double, rounded once.
+struct NodeAcc {            // 64 bytes per node
+    int32_t cnt[8];
+    unsigned long long bytes;
+    long long first, last;  // bit patterns of non-negative doubles (monotone as signed integers)
+    int32_t flags;          // NERRF_PATH_* bits | 0x100 = label
+    int32_t deg;            // in-degree == out-degree: every event adds each edge in both directions
+};
+
+__global__ void __launch_bounds__(256) node_acc_init_kernel(NodeAcc* __restrict__ acc, int64_t N) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < N; v += stride) {
+        NodeAcc a;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.cnt[k] = 0;
+        a.bytes = 0ull; a.first = 0x7fffffffffffffffll; a.last = -0x7fffffffffffffffll - 1; a.flags = 0; a.deg = 0;
+        acc[v] = a;
+    }
+}
+
+__device__ __forceinline__ void touch(NodeAcc* __restrict__ acc, int32_t v, int slot, unsigned long long size, long long tb, int deg) {
+    NodeAcc* a = acc + v;
+    atomicAdd(&a->cnt[slot], 1);
+    if (size) atomicAdd(&a->bytes, size);
+    atomicMin(&a->first, tb);
+    atomicMax(&a->last, tb);
+    atomicAdd(&a->deg, deg);
+}
+
+__global__ void __launch_bounds__(256) node_acc_events_kernel(const int32_t* __restrict__ node_p, const int32_t* __restrict__ node_f,
+                                                               const int32_t* __restrict__ node_g, const double* __restrict__ t,
+                                                               const uint8_t* __restrict__ slot, const uint64_t* __restrict__ bytes,
+                                                               const uint8_t* __restrict__ pflags, int64_t n, int64_t N,
+                                                               NodeAcc* __restrict__ acc, int* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t p = node_p[i], f = node_f[i], g = node_g ? node_g[i] : -1;
+        const double ti = t[i];
+        if ((uint32_t)p >= (uint64_t)N || (uint32_t)f >= (uint64_t)N || g < -1 || (int64_t)g >= N || !(ti >= 0.0) || slot[i] > 7) {
+            *bad = 1;
+            continue;
+        }
+        const long long tb = __double_as_longlong(ti + 0.0);
+        const int s = slot[i];
+        const unsigned long long sz = bytes[i];
+        touch(acc, p, s, sz, tb, 1);
+        touch(acc, f, s, sz, tb, g >= 0 ? 2 : 1);
+        if (g >= 0) touch(acc, g, s, sz, tb, 1);
+        const int fl = (int)pflags[i] | ((s == 1 || s == 2) ? 0x100 : 0);
+        if (fl) atomicOr(&acc[f].flags, fl);
+    }
+}
+
+__global__ void __launch_bounds__(256) node_features_kernel(const NodeAcc* __restrict__ acc, const int8_t* __restrict__ kind,
+                                                             int64_t N, double window, float* __restrict__ x,
+                                                             int32_t* __restrict__ label, float* __restrict__ size_mb) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < N; v += stride) {
+        const NodeAcc a = acc[v];
+        float row[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) row[k] = 0.f;
+        const bool is_file = kind[v] == 0;
+        row[0] = is_file ? 1.f : 0.f;
+        row[1] = kind[v] == 1 ? 1.f : 0.f;
+        const float d = (float)log1p((double)a.deg);
+        row[3] = d; row[4] = d;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) row[5 + k] = (float)log1p((double)a.cnt[k]);
+        const double nb = (double)a.bytes;
+        row[13] = (float)(log1p(nb) / 20.0);
+        const double first = __longlong_as_double(a.first), last = __longlong_as_double(a.last);
+        row[14] = (float)((last - first) / window);
+        row[15] = (float)(first / window);
+        row[16] = (a.flags & NERRF_PATH_LOCKBIT) ? 1.f : 0.f;
+        row[17] = (a.flags & NERRF_PATH_NOTE) ? 1.f : 0.f;
+        row[18] = (a.flags & NERRF_PATH_TMP) ? 1.f : 0.f;
+        const double wr = (double)a.cnt[1] + (double)a.cnt[5];
+        row[19] = wr > 0.0 ? (float)((double)a.cnt[2] / wr) : 0.f;
+        float4* out = reinterpret_cast<float4*>(x + v * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+        if (label) label[v] = (a.flags & 0x100) ? 1 : 0;
+        if (size_mb) {
+            const double k3 = fmax((double)a.cnt[0] + (double)a.cnt[1] + (double)a.cnt[2], 1.0);
+            size_mb[v] = is_file ? (float)(nb / k3 / 1e6) : 0.f;
+        }
+    }
+}
+
 struct CsrWs {
     size_t keys_a, keys_b, vals_a, vals_b, bad, temp, total, temp_bytes;
 };
@@ -182,5 +277,44 @@ extern "C" int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, con
     NERRF_CHECK_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
     NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
     NERRF_REQUIRE(h_bad == 0, "edge list holds a vertex id outside [0, n_nodes)");
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_graph_node_features_workspace_bytes(int64_t n_nodes, int64_t* bytes) {
+    NERRF_REQUIRE(bytes != nullptr && n_nodes >= 1, "bad arguments");
+    *bytes = (int64_t)up256((size_t)n_nodes * sizeof(NodeAcc)) + 256;
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_graph_node_features(const int32_t* node_p, const int32_t* node_f, const int32_t* node_g, const double* t,
+                                         const uint8_t* event_slot, const uint64_t* bytes, const uint8_t* path_flags,
+                                         int64_t n_events, const int8_t* node_kind, int64_t n_nodes, double window, float* x_out,
+                                         int32_t* label_out, float* size_mb_out, void* workspace, int64_t workspace_bytes,
+                                         void* stream) {
+    NERRF_REQUIRE(n_events >= 0 && n_nodes >= 1 && n_nodes < ((int64_t)1 << 31), "bad sizes");
+    NERRF_REQUIRE((n_events == 0 || (node_p && node_f && t && event_slot && bytes && path_flags)) && node_kind && x_out,
+                  "null pointer");
+    NERRF_REQUIRE(window > 0.0, "window must be positive");
+    int64_t need = 0;
+    nerrf_graph_node_features_workspace_bytes(n_nodes, &need);
+    NERRF_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: %lld < %lld bytes",
+                  (long long)workspace_bytes, (long long)need);
+    NERRF_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x_out & 15) == 0, "workspace / x_out misaligned");
+    static_assert(sizeof(NodeAcc) == 64, "NodeAcc layout");
+    cudaStream_t st = (cudaStream_t)stream;
+    NodeAcc* acc = (NodeAcc*)workspace;
+    int* bad = (int*)((char*)workspace + up256((size_t)n_nodes * sizeof(NodeAcc)));
+    const int grid = sm_count() * 8;
+    NERRF_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+    node_acc_init_kernel<<<grid, 256, 0, st>>>(acc, n_nodes);
+    if (n_events) node_acc_events_kernel<<<grid, 256, 0, st>>>(node_p, node_f, node_g, t, event_slot, bytes, path_flags, n_events,
+                                                                n_nodes, acc, bad);
+    node_features_kernel<<<grid, 256, 0, st>>>(acc, node_kind, n_nodes, window, x_out, label_out, size_mb_out);
+    const int rc = launch_status("node feature kernels");
+    if (rc != NERRF_OK) return rc;
+    int h_bad = 0;
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
+    NERRF_REQUIRE(h_bad == 0, "event columns hold a node id outside [0, n_nodes), a negative time or an event slot > 7");
     return NERRF_OK;
 }

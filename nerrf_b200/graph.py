@@ -89,6 +89,40 @@ def build_csr_device(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU, rowptr_dtype=N
     return rowptr, col, ew
 
 
+def node_features_device(node_p, node_f, node_g, t, event_slot, nbytes, path_flags, node_kind, window):
+    """Device per-node features (include/nerrf_b200.h nerrf_graph_node_features).  CUDA tensors: int32 node ids per
+    event (node_g may be None), float64 t (seconds since the first event), uint8 event_slot / path_flags, int64|uint64
+    byte counts, int8 node_kind [N].  -> x fp32 [N, 32], label int32 [N], size_mb fp32 [N] (CUDA).  No CPU fallback."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    _lib.require_cuda(node_p, node_f, node_g, t, event_slot, nbytes, path_flags, node_kind)
+    want = ((node_p, torch.int32), (node_f, torch.int32), (t, torch.float64), (event_slot, torch.uint8),
+            (path_flags, torch.uint8), (node_kind, torch.int8))
+    for a, dt in want:
+        if a.dtype != dt or not a.is_contiguous():
+            raise TypeError(f"node_features_device: expected contiguous {dt}, got {a.dtype}")
+    if node_g is not None and (node_g.dtype != torch.int32 or not node_g.is_contiguous()):
+        raise TypeError("node_g must be contiguous int32")
+    if nbytes.dtype not in (torch.int64, torch.uint64) or not nbytes.is_contiguous():
+        raise TypeError("nbytes must be contiguous int64 / uint64")
+    n, N, dev = int(node_p.shape[0]), int(node_kind.shape[0]), node_p.device
+    h = _lib.lib()
+    with torch.cuda.device(dev):
+        need = C.c_int64()
+        _lib.check(h.nerrf_graph_node_features_workspace_bytes(N, C.byref(need)), "nerrf_graph_node_features_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        x = torch.empty(N, F_IN, dtype=torch.float32, device=dev)
+        label = torch.empty(N, dtype=torch.int32, device=dev)
+        size_mb = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.check(h.nerrf_graph_node_features(_lib.ptr(node_p), _lib.ptr(node_f), _lib.ptr(node_g), _lib.ptr(t),
+                                               _lib.ptr(event_slot), _lib.ptr(nbytes), _lib.ptr(path_flags), n,
+                                               _lib.ptr(node_kind), N, float(window), _lib.ptr(x), _lib.ptr(label),
+                                               _lib.ptr(size_mb), _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr()),
+                   "nerrf_graph_node_features")
+    return x, label, size_mb
+
+
 def synthetic_graph(N=1_000_000, E=10_000_000, seed=20250115, hub="src", feat_seed=0, f_in=F_IN) -> TemporalGraph:
     """SURVEY.md 8d cfg 2/4 generator: dst ~ U{0..N-1}, src = floor(N*u^3) (hub sources, one
     ransomware pid touching many files); hub="dst" swaps the roles (long rows)."""

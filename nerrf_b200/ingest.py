@@ -118,9 +118,10 @@ def _node_names(cols, name_event, name_which):
 
 def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, device=None) -> G.TemporalGraph:
     """Same graph as graph.graph_from_events(events_from_columns(cols)) -- nodes, numbering, CSR, weights, features,
-    labels -- without a per-event Python loop.  device=None: arrays are numpy (host CSR stage).  device="cuda[:i]":
-    the edge sort / CSR / temporal weights run on the GPU (graph.build_csr_device) and rowptr, col, ew, x are CUDA
-    tensors ready for GraphSAGE_T.forward."""
+    labels -- without a per-event Python loop.  device=None: arrays are numpy (host stages).  device="cuda[:i]":
+    the per-node features (graph.node_features_device) and the edge sort / CSR / temporal weights
+    (graph.build_csr_device) run on the GPU; rowptr, col, ew, x are CUDA tensors ready for GraphSAGE_T.forward
+    (rowptr / col / labels identical to the host path, ew and x within the rounding of exp / log1p)."""
     n = cols.n
     if n == 0:
         raise ValueError("empty trace")
@@ -144,6 +145,21 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     src = src4.ravel()[keep]; dst = dst4.ravel()[keep]
     tt = np.repeat(t, 4)[keep].astype(np.float32)
     conf = np.ones(src.shape[0], np.float32)
+
+    names = _node_names(cols, name_event, name_which)
+    meta = {"kind": "trace", "names": names, "node_kind": kind.astype(np.int64), "t0": t0, "span": span}
+    if device is not None:
+        # device path: features by integer atomics + one node pass, edges sorted into CSR by the radix-sort stage
+        import torch
+        dev = torch.device(device)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt, copy=False))).to(dev)
+        x, label, size_mb = G.node_features_device(up(P, np.int32), up(F, np.int32), up(Gn, np.int32) if has_g.any() else None,
+                                                   up(t, np.float64), up(slot, np.uint8), up(cols.bytes[order], np.int64),
+                                                   up(pf, np.uint8), up(kind, np.int8), window)
+        rowptr, col, ew = G.build_csr_device(up(src, np.int32), up(dst, np.int32), up(tt, np.float32), up(conf, np.float32), N,
+                                             t_ref=float(span), tau=G.TAU)
+        meta.update(label=label.cpu().numpy().astype(np.int64), size_mb=size_mb.cpu().numpy(), device=str(dev))
+        return G.TemporalGraph(rowptr, col, ew, x, meta)
 
     # per-node features over the touched nodes (p, f [, g]) of every event
     tn = np.concatenate([P, F, Gn[has_g]]); tslot = np.concatenate([slot, slot, slot[has_g]])
@@ -171,19 +187,9 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     k = np.maximum(cnt[:, 0] + cnt[:, 1] + cnt[:, 2], 1.0)
     size_mb = np.where(kind == 0, nbytes / k / 1e6, 0.0).astype(np.float32)
 
-    names = _node_names(cols, name_event, name_which)
-    meta = {"kind": "trace", "names": names, "node_kind": kind.astype(np.int64), "label": label, "size_mb": size_mb,
-            "t0": t0, "span": span}
-    if device is None:
-        rowptr, col, ew = G.csr_from_edges(src, dst, tt, conf, N, t_ref=float(span), tau=G.TAU)
-        return G.TemporalGraph(rowptr, col, ew, x, meta)
-    import torch
-    dev = torch.device(device)
-    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev)
-    rowptr, col, ew = G.build_csr_device(up(src, np.int32), up(dst, np.int32), up(tt, np.float32), up(conf, np.float32), N,
-                                         t_ref=float(span), tau=G.TAU)
-    meta["device"] = str(dev)
-    return G.TemporalGraph(rowptr, col, ew, torch.from_numpy(x).to(dev), meta)
+    meta.update(label=label, size_mb=size_mb)
+    rowptr, col, ew = G.csr_from_edges(src, dst, tt, conf, N, t_ref=float(span), tau=G.TAU)
+    return G.TemporalGraph(rowptr, col, ew, x, meta)
 
 
 # ------------------------------------------------------------------ test / tooling helper (not on the product path)

@@ -119,6 +119,53 @@ def test_reference_trace_graphs_rebuild_from_shuffled_edges(name):
     assert np.array_equal(rp, rowptr) and np.array_equal(c2, col) and np.array_equal(w2, ew)   # exp(~0) == 1 exactly
 
 
+def _features_close(dev, host):
+    # x: counts / flags / ratios exact; log1p columns within 1 ulp of fp32 (CUDA's and the host's double log1p
+    # can differ in the last bit of the double, which survives the fp32 rounding only at a tie)
+    xd = dev.x.cpu().numpy()
+    assert xd.shape == host.x.shape
+    assert np.all(np.abs(xd - host.x) <= np.spacing(np.abs(host.x))), np.argwhere(xd != host.x)[:5]
+    exact = [0, 1, 2, 14, 15, 16, 17, 18, 19] + list(range(20, 32))
+    assert np.array_equal(xd[:, exact], host.x[:, exact])
+    assert np.array_equal(dev.meta["label"], host.meta["label"])
+    assert np.array_equal(dev.meta["size_mb"], host.meta["size_mb"])
+
+
+@pytest.mark.parametrize("merge", [True, False])
+def test_device_constructor_on_unordered_stream_with_rename_targets(merge):
+    from nerrf_b200 import ingest
+    rng = np.random.default_rng(12)
+    ev = []
+    for i in range(3000):
+        kind = ["openat", "write", "rename", "file_encrypt_start", "file_encrypt_complete", "unlink"][int(rng.integers(6))]
+        stem = "/app/uploads/f%d" % rng.integers(150)
+        e = {"ts": (1_700_000_000 + int(rng.integers(0, 55)), int(rng.integers(0, 8)) * 125_000_000), "pid": int(rng.integers(1, 6)),
+             "syscall": kind, "path": stem + [".dat", ".lockbit3", ""][int(rng.integers(3))], "bytes": int(rng.integers(0, 1 << 22))}
+        if kind == "rename":
+            e["new_path"] = "/app/uploads/f%d.lockbit3" % rng.integers(150)
+        ev.append(e)
+    cols = ingest.decode_event_batch(ingest.encode_event_batch(ev))
+    host = ingest.graph_from_columns(cols, merge_renames=merge)
+    dev = ingest.graph_from_columns(cols, merge_renames=merge, device="cuda")
+    assert np.array_equal(dev.rowptr.cpu().numpy(), host.rowptr) and np.array_equal(dev.col.cpu().numpy(), host.col)
+    assert np.all(np.abs(dev.ew.cpu().numpy() - host.ew) <= 6 * np.spacing(np.abs(host.ew)))
+    _features_close(dev, host)
+    assert dev.meta["names"] == host.meta["names"]
+
+
+def test_node_features_reject_bad_columns():
+    i32 = lambda *v: torch.tensor(v, dtype=torch.int32).cuda()
+    args = dict(node_p=i32(0, 0), node_f=i32(1, 5), node_g=None, t=torch.tensor([0.0, 1.0], dtype=torch.float64).cuda(),
+                event_slot=torch.tensor([4, 5], dtype=torch.uint8).cuda(), nbytes=torch.tensor([1, 2]).cuda(),
+                path_flags=torch.zeros(2, dtype=torch.uint8).cuda(), node_kind=torch.tensor([1, 0], dtype=torch.int8).cuda(), window=60.0)
+    with pytest.raises(NerrfError, match="outside"):
+        G.node_features_device(**args)
+    args["node_f"] = i32(1, 1)
+    x, label, size_mb = G.node_features_device(**args)
+    assert x.shape == (2, 32) and label.tolist() == [0, 0] and float(x[1, 5 + 4]) == pytest.approx(np.log1p(1.0))
+    assert float(size_mb[1]) == pytest.approx(3.0 / 1e6) and float(x[0, 3]) == pytest.approx(np.log1p(2.0))
+
+
 def test_wire_bytes_to_device_graph_to_plan():
     # EventBatch wire bytes -> columns -> graph with the CSR stage on the GPU -> the same graph as the host path,
     # and the pipeline runs on the device-resident graph without another upload
@@ -131,7 +178,7 @@ def test_wire_bytes_to_device_graph_to_plan():
     assert dev.rowptr.is_cuda and dev.x.is_cuda and dev.num_nodes == host.num_nodes
     assert np.array_equal(dev.rowptr.cpu().numpy(), host.rowptr) and np.array_equal(dev.col.cpu().numpy(), host.col)
     assert np.all(np.abs(dev.ew.cpu().numpy() - host.ew) <= 6 * np.spacing(np.abs(host.ew)))
-    assert np.array_equal(dev.x.cpu().numpy(), host.x)
+    _features_close(dev, host)
     seq, lengths, nodes = pipeline.file_sequences(ingest.events_from_columns(cols), host)
     label = host.meta["label"].astype(bool)
     model = GraphSAGE_T(32, 128, 2).cuda(); seq_model = lstm.LSTMScorer().cuda()
