@@ -192,6 +192,46 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     return G.TemporalGraph(rowptr, col, ew, x, meta)
 
 
+def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None):
+    """Per-file event sequences for the LSTM without per-event Python: the same arrays as
+    pipeline.file_sequences(events_from_columns(cols), graph) -- seq fp32 [n_files, t_max, 16], lengths int32, node ids --
+    (the last t_max events of every file node, oldest first; feature layout: pipeline.file_sequences)."""
+    from .ai.models import lstm
+    t_max = t_max or lstm.T_MAX
+    n = cols.n
+    ts = cols.timestamp
+    order = np.argsort(ts, kind="stable")
+    t0 = float(ts[order[0]]) if n else 0.0
+    span = max(float(ts[order[-1]]) - t0, 1e-6) if n else 1.0
+    _, node_f, _, kind, _, _ = intern_nodes(cols, order, merge_renames)
+    F = node_f[order].astype(np.int64)
+    tt = ts[order]                                        # absolute seconds, time-sorted
+    # group by file node, keeping time order inside a group
+    by_file = np.argsort(F, kind="stable")
+    Fg = F[by_file]
+    nodes, start, count = np.unique(Fg, return_index=True, return_counts=True)
+    pos = np.arange(n) - np.repeat(start, count)          # rank of the event inside its file's history
+    keep_from = np.repeat(np.maximum(count - t_max, 0), count)
+    sel = pos >= keep_from                                # the last t_max events
+    row = np.repeat(np.arange(nodes.size), count)[sel]
+    k = (pos - keep_from)[sel]
+    ev = by_file[sel]                                     # index into the time-sorted arrays
+    seq = np.zeros((nodes.size, t_max, lstm.D_IN), np.float32)
+    lengths = np.minimum(count, t_max).astype(np.int32)
+    slot = cols.event_slot[order][ev].astype(np.int64)
+    seq[row, k, slot] = 1.0
+    seq[row, k, 8] = np.log1p(cols.bytes[order][ev].astype(np.float64)) / 20.0
+    prev_t = np.empty(n); prev_t[1:] = tt[by_file][:-1]; prev_t[0] = 0.0
+    dt = np.minimum(tt[by_file] - prev_t, 10.0)
+    dt[(pos == keep_from)] = 0.0                          # first kept event of a file has no predecessor in the window
+    seq[row, k, 9] = dt[sel]
+    seq[row, k, 10] = (tt[ev] - t0) / span
+    pf = cols.path_flags[order][ev]
+    seq[row, k, 11] = (pf & 1) != 0
+    seq[row, k, 12] = (pf & 4) != 0
+    return seq, lengths, nodes.astype(np.int64)
+
+
 # ------------------------------------------------------------------ test / tooling helper (not on the product path)
 def encode_event_batch(events) -> bytes:
     """Minimal protobuf WRITER for nerrf.trace.EventBatch (proto3 canonical form: default-valued fields omitted),

@@ -27,7 +27,8 @@ _SEQ_EVENT_SLOT = {"file_created": 0, "file_encrypt_start": 1, "file_encrypt_com
 def file_sequences(events, g: G.TemporalGraph, t_max=lstm.T_MAX):
     """Per-file event sequences for the LSTM (the last `t_max` events of each file node, oldest first).
     Features (D_in = 16): one-hot event kind (8), log1p(size)/20, dt to the previous event of the file (s, clipped),
-    time since trace start / window, .lockbit flag, /tmp|/proc flag, attack-phase flag, 2 spare."""
+    time since trace start / window, .lockbit flag, /tmp|/proc flag, 3 spare (the simulator's `phase` annotation is
+    ground truth, not an observable: it is deliberately NOT a feature, so wire-format traces give the same sequences)."""
     names = {n: i for i, n in enumerate(g.meta["names"])}
     stem_of = {G._stem(n): i for n, i in names.items()}
     evs = sorted(events, key=lambda e: G._parse_ts(e["timestamp"]))
@@ -54,7 +55,6 @@ def file_sequences(events, g: G.TemporalGraph, t_max=lstm.T_MAX):
             seq[i, k, 10] = (t - t0) / span
             seq[i, k, 11] = 1.0 if ".lockbit" in e["path"] else 0.0
             seq[i, k, 12] = 1.0 if e["path"].startswith(("/tmp", "/proc")) else 0.0
-            seq[i, k, 13] = 1.0 if e.get("phase") == "attack" else 0.0
             prev = t
     return seq, lengths, np.asarray(nodes, np.int64)
 

@@ -156,3 +156,24 @@ def test_replayed_m1_style_trace_scales_without_python_loops():
     cols = ingest.decode_event_batch(wire)
     g = ingest.graph_from_columns(cols)
     assert cols.n == len(ev) and g.num_nodes > 50 * 40 and g.meta["label"].sum() == 50 * 40
+
+
+def test_columnar_sequences_equal_per_event_sequences():
+    from nerrf_b200 import pipeline
+    ev = G.replicate_events(trace_sim.lockbit_trace(n_files=12, seed=5, benign_files=9), 3)
+    rng = np.random.default_rng(0)
+    hot = ev[40]["path"]                                  # one file with a long history: exercises the last-100 window
+    t_hot = G._parse_ts(ev[-1]["timestamp"])
+    for i in range(130):
+        ev.append({"timestamp": t_hot + 0.01 * (i + 1) + float(rng.random()) * 0.001, "event": "write", "path": hot,
+                   "size": int(rng.integers(1, 1 << 20)), "pid": 7})
+    for e in ev:
+        e.pop("phase", None)                              # the wire format carries no phase
+        e["timestamp"] = G._parse_ts(e["timestamp"])
+    cols = ingest.decode_event_batch(ingest.encode_event_batch(ev))
+    events = ingest.events_from_columns(cols)
+    g = ingest.graph_from_columns(cols)
+    want_seq, want_len, want_nodes = pipeline.file_sequences(events, g)
+    seq, lengths, nodes = ingest.sequences_from_columns(cols)
+    assert np.array_equal(nodes, want_nodes) and np.array_equal(lengths, want_len) and lengths.max() == 100
+    assert np.array_equal(seq.view(np.uint32), want_seq.view(np.uint32)), np.argwhere(seq != want_seq)[:5]

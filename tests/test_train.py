@@ -63,3 +63,16 @@ def test_m2_gate_on_the_reference_traces(trained, name):
     files = z[name + "_kind"] == 0
     auc = T.roc_auc(logit.numpy()[files], z[name + "_label"][files])
     assert auc >= 0.90, auc
+
+
+def test_checkpoint_round_trip_into_the_undo_cli_loader(tmp_path):
+    from nerrf_b200 import undo
+    out = str(tmp_path / "w.pt")
+    T.main(["--traces", "2", "--epochs", "2", "--out", out])
+    model, scorer = undo.load_models(out, 0)
+    ck = torch.load(out, map_location="cpu")
+    assert model.num_layers == ck["layers"] == 2
+    assert all(torch.equal(v, ck["sage"][k]) for k, v in model.state_dict().items())
+    assert all(torch.equal(v, ck["lstm"][k]) for k, v in scorer.state_dict().items())
+    with pytest.raises(SystemExit, match="no weights"):
+        undo.load_models(None, 0)
