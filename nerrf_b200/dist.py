@@ -219,7 +219,7 @@ def cuda_layer_fn(model):
 def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, algorithmic_bytes_layer, measured_peaks,
                   ClockSampler, physical_gpu_index, run_mcts_bench):
     """bench.py's N > 1 arm (weak scaling: N x (1M nodes, 10M edges), one exchange per layer)."""
-    from bench import N_NODES, N_EDGES, HIDDEN, LAYERS, F_IN
+    from bench import N_NODES, N_EDGES, HIDDEN, LAYERS
     N, E = N_NODES * world, N_EDGES * world
     rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, relabel=True)
     shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")

@@ -12,11 +12,9 @@ emit.  Everything between the graph and the plan runs in the CUDA kernels; there
 from __future__ import annotations
 
 import argparse
-import json
 import sys
 import time
 
-import numpy as np
 import torch
 
 from . import graph as G, ingest, pipeline

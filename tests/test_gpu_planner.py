@@ -1,7 +1,6 @@
 """rewards.score and mcts.search CUDA path vs the oracle: BIT-EXACT (needs a B200)."""
 import numpy as np
 import pytest
-import torch
 
 from nerrf_b200.ai.planner import mcts, rewards
 from nerrf_b200.ai.planner.rewards import Actions

@@ -1,7 +1,6 @@
 """`python -m nerrf_b200.undo`: EventBatch wire file in, undo plan out (needs a B200)."""
 import json
 
-import numpy as np
 import pytest
 
 from nerrf_b200 import ingest, trace_sim, undo

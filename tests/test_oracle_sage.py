@@ -1,5 +1,4 @@
 """Known-answer tests for the GraphSAGE-T oracle (CPU)."""
-import numpy as np
 import torch
 
 from oracle import sage_ref as S
