@@ -12,6 +12,13 @@
 
 namespace nerrf {
 
+// tensor-core path (lstm_umma.cu), selected with NERRF_LSTM_ALGO=umma
+bool lstm_umma_enabled();
+size_t lstm_umma_workspace_bytes(int64_t B, int T);
+int lstm_layers_umma(const float* seq, const int32_t* len, int64_t B, int T, int D_in, int num_layers, const float* const* Wih_t,
+                     const float* const* Whh_t, const float* const* bias, float* hfin, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st);
+
 constexpr int LH = 256;       // hidden size (threads per CTA)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -158,6 +165,7 @@ extern "C" int nerrf_lstm_workspace_bytes(int64_t B, int T, int H, size_t* bytes
     NERRF_REQUIRE(bytes, "null out");
     NERRF_REQUIRE(B >= 0 && T >= 1 && H == LH, "LSTM: need B >= 0, T >= 1, H == 256");
     *bytes = ((size_t)2 * B * T * 2 * H + (size_t)B * 2 * H) * sizeof(float) + 256;
+    if (lstm_umma_enabled() && B > 0) *bytes = lstm_umma_workspace_bytes(B, T) + (size_t)B * 2 * H * sizeof(float) + 512;
     return NERRF_OK;
 }
 
@@ -177,6 +185,16 @@ extern "C" int nerrf_lstm_forward(const float* seq, const int32_t* len, int64_t 
     }
     if (B == 0) return NERRF_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (lstm_umma_enabled()) {
+        // workspace = [hfin | tensor-core scratch]
+        float* hf = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        char* scratch = (char*)hf + (((size_t)B * 2 * H * sizeof(float) + 255) & ~(size_t)255);
+        const size_t left = workspace_bytes - (size_t)(scratch - (char*)workspace);
+        rc = lstm_layers_umma(seq, len, B, T, D_in, num_layers, Wih_t, Whh_t, bias, hf, scratch, left, st);
+        if (rc) return rc;
+        lstm_head_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(hf, head_W, head_b, out, B, 2 * H);
+        return launch_status("lstm_head_kernel");
+    }
     float* buf0 = (float*)workspace;
     float* buf1 = buf0 + (size_t)B * T * 2 * H;
     float* hfin = buf1 + (size_t)B * T * 2 * H;
