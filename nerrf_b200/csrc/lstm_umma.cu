@@ -22,7 +22,8 @@
 // Groups are independent (no grid barrier): group g owns direction g & 1 and the sequence tiles (g >> 1) + k * G/2.
 // The 8 CTAs of a group must be co-resident: cooperative launch, one CTA per SM, grid = 8 * G <= #SMs.
 //
-// STATUS: written against the validated sage_umma.cu building blocks, cross-compiled, NOT YET RUN on hardware.
+// STATUS: parity-green on B200 against the oracle (max err 1.2e-7 on B=6/130/300; scripts/lstm_umma_check.py); first
+// timing 56 ms for B=4096, T=100 (v0 FFMA kernel: 52 ms) -- opt-in (NERRF_LSTM_ALGO=umma) until it is faster.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -82,6 +83,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin) {
         if (spin > (1u << 16)) __nanosleep(64);
         if (spin > (1u << 26)) __trap();
+    }
+}
+// roles with slack poll with a sleep so they do not take issue slots from the producer warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin) {
+        __nanosleep(100);
+        if (spin > (1u << 25)) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -280,21 +288,32 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_umma_kernel(RecArgs P) {
 
             auto init_acc = [&](int step) {        // accumulator <- G_x[:, t] for this thread's gate row, 64 sequences
                 const int t = dir ? (P.T - 1 - step) : step;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    // the 16 (or 32) loads of a chunk are issued back to back: rows past the batch are clamped (their
+                    // sequences have length 0, the value is never used), so there is no branch between the loads
+                    float ga[16];
+                    const int64_t bb = b0 + half * 64 + c * 16;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t b = b0 + half * 64 + c * 32 + j;
-                        float g = 0.f;
-                        if (b < P.B) {
-                            const size_t off = (size_t)(b * P.T + t) * UM + gcol;
-                            g = __ldg(gxa + off);
-                            if (gxb) g += __ldg(gxb + off);
-                        }
-                        v[j] = __float_as_uint(g);
+                    for (int j = 0; j < 16; ++j) {
+                        const int64_t b = (bb + j < P.B) ? bb + j : P.B - 1;
+                        ga[j] = __ldg(gxa + (size_t)(b * P.T + t) * UM + gcol);
                     }
-                    tmem_st32(acc_addr + (uint32_t)(c * 32), v);
+                    if (gxb) {
+                        float gb[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int64_t b = (bb + j < P.B) ? bb + j : P.B - 1;
+                            gb[j] = __ldg(gxb + (size_t)(b * P.T + t) * UM + gcol);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) ga[j] += gb[j];
+                    }
+                    uint32_t v0[8], v1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v0[j] = __float_as_uint(ga[j]); v1[j] = __float_as_uint(ga[8 + j]); }
+                    tmem_st8(acc_addr + (uint32_t)(c * 16), v0);
+                    tmem_st8(acc_addr + (uint32_t)(c * 16 + 8), v1);
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_umma_kernel(RecArgs P) {
 
             for (int step = 0; step < P.T; ++step, ++q) {
                 const int t = dir ? (P.T - 1 - step) : step;
-                mbar_wait(accf_bar, q & 1u);
+                mbar_wait_relaxed(accf_bar, q & 1u);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -367,7 +386,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_umma_kernel(RecArgs P) {
             const uint32_t d_tmem = tmem_base + (uint32_t)ACC_COL0;
             const uint32_t total = (uint32_t)(n_items * P.T);
             for (uint32_t q = 0; q < total; ++q) {
-                mbar_wait(accinit_bar, q & 1u);                      // accumulator holds G_x[:, t]
+                mbar_wait_relaxed(accinit_bar, q & 1u);              // accumulator holds G_x[:, t]
                 mbar_wait(opfull_bar, q & 1u);                       // B operand holds h_{t-1}
                 tc_fence_after();
 #pragma unroll 2
@@ -417,15 +436,22 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_umma_kernel(RecArgs P) {
                     }
                 } else {
                     const float* src = hx + (size_t)((q - 1) & 1u) * NSEQ * LH;
-#pragma unroll 4
-                    for (int i = pt; i < NSEQ * (LH / 4); i += PROD_WARPS * 32) {
-                        const float4 v = ld_cg4(src + (size_t)i * 4);
-                        uint32_t lo[NS], hi[NS];
-                        split_pair(v.x, v.y, lo);
-                        split_pair(v.z, v.w, hi);
-                        const uint32_t off = b_offset(i >> 6, (i & 63) * 4);
+                    constexpr int PB = 8;                                   // float4 loads in flight per thread
+                    for (int i0 = pt; i0 < NSEQ * (LH / 4); i0 += PB * PROD_WARPS * 32) {
+                        float4 v[PB];
 #pragma unroll
-                        for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(smem_gen + p * PART_BYTES + off) = make_uint2(lo[p], hi[p]);
+                        for (int u = 0; u < PB; ++u) v[u] = ld_cg4(src + (size_t)(i0 + u * PROD_WARPS * 32) * 4);
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) {
+                            const int i = i0 + u * PROD_WARPS * 32;
+                            uint32_t lo[NS], hi[NS];
+                            split_pair(v[u].x, v[u].y, lo);
+                            split_pair(v[u].z, v[u].w, hi);
+                            const uint32_t off = b_offset(i >> 6, (i & 63) * 4);
+#pragma unroll
+                            for (int p = 0; p < NS; ++p)
+                                *reinterpret_cast<uint2*>(smem_gen + p * PART_BYTES + off) = make_uint2(lo[p], hi[p]);
+                        }
                     }
                 }
                 fence_proxy_async();
