@@ -376,8 +376,23 @@ def run_lstm_bench(dev, B=4096, T=100):
     e0.record(); model(seq, lengths); model(seq, lengths); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 2
     flops = B * T * 2.0 * (2 * 1024 * (16 + 256) + 2 * 1024 * (512 + 256))      # both directions, both layers
-    return {"metric": "lstm_sequences_per_sec", "value": B / (ms * 1e-3), "unit": "sequences/s", "ms": ms,
-            "tflops_fp32": flops / (ms * 1e-3) / 1e12, "config": {"batch": B, "T": T, "hidden": 256, "layers": 2}}
+    info = {"metric": "lstm_sequences_per_sec", "value": B / (ms * 1e-3), "unit": "sequences/s", "ms": ms,
+            "tflops_fp32": flops / (ms * 1e-3) / 1e12, "config": {"batch": B, "T": T, "hidden": 256, "layers": 2},
+            "algo": "ffma (default)"}
+    # opt-in tensor-core path (csrc/lstm_umma.cu): same entry point, NERRF_LSTM_ALGO=umma; reported beside the default
+    try:
+        ref = model(seq, lengths)
+        os.environ["NERRF_LSTM_ALGO"] = "umma"
+        got = model(seq, lengths); torch.cuda.synchronize()
+        e0.record(); model(seq, lengths); model(seq, lengths); e1.record(); torch.cuda.synchronize()
+        ms_u = e0.elapsed_time(e1) / 2
+        info["umma"] = {"value": B / (ms_u * 1e-3), "unit": "sequences/s", "ms": ms_u,
+                        "max_abs_diff_vs_default": float((got - ref).abs().max())}
+    except Exception as e:                          # the default path above is the reported number either way
+        info["umma"] = {"error": str(e)[:200]}
+    finally:
+        os.environ.pop("NERRF_LSTM_ALGO", None)
+    return info
 
 
 def run_graph_build_bench(dev, rowptr, col, reps=3):
