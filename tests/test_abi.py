@@ -87,3 +87,19 @@ def test_reference_named_surface_imports():
     from ai.planner import mcts, rewards
     assert callable(mcts.search) and callable(rewards.score) and callable(lstm.forward)
     assert hasattr(GraphSAGE_T, "forward")
+
+
+def test_header_is_plain_c99(tmp_path, lib_built):
+    """The boundary is a C ABI: the header must compile as C (no C++-isms), and a C program must link against the
+    library with nothing but -lnerrf_b200 (static cudart inside)."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "nerrf_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", nerrf_abi_version(), nerrf_last_error()); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(lib_built)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lnerrf_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "1"
