@@ -222,9 +222,12 @@ int nerrf_graph_node_features(const int32_t* node_p, const int32_t* node_f, cons
  * 1 file_encrypt_start, 2 file_encrypt_complete, 3 ransom_note_created, 4 openat, 5 write,
  * 6 rename, 7 other); path_flags = NERRF_PATH_* bits of `path`.  Malformed input ->
  * NERRF_ERR_INVALID with the byte offset in nerrf_last_error().
+ * Events must name a file: the tracker zeroes `path` on write events (tracker/bpf/tracepoints.c:62-64); the host
+ * side (nerrf_b200/ingest.py resolve_columns) attributes those to the pid's last non-empty path before interning.
  * nerrf_trace_intern: pid / path interning ("merge by inode", architecture.mdx:41): node ids in
  * order of first appearance over events visited in `order` (NULL = as stored); node tables sized
- * by the caller (node_capacity >= 2*n_events with merge_renames, 3*n_events without);
+ * by the caller (node_capacity >= 2*n_events with merge_renames, 3*n_events without); with merge_renames a
+ * non-empty new_path aliases its merge key to the event's file node (a real rename a.dat -> a.dat.lockbit3);
  * node_name_which: 0 = path, 1 = new_path of event node_name_event, 2 = the pid itself. */
 #define NERRF_PATH_LOCKBIT   1   /* ".lockbit" in path */
 #define NERRF_PATH_NOTE      2   /* README / RANSOM (ASCII case-insensitive) in path */
@@ -237,6 +240,9 @@ int nerrf_trace_decode(const uint8_t* buf, int64_t len, int64_t n_events,
                        uint8_t* event_slot, uint8_t* path_flags,
                        int64_t* comm_off, uint8_t* comm_data, int64_t* syscall_off, uint8_t* syscall_data,
                        int64_t* path_off, uint8_t* path_data, int64_t* new_path_off, uint8_t* new_path_data);
+/* NERRF_PATH_* bits for every string of a packed string column (off [n+1], data): the rule nerrf_trace_decode
+ * applies to `path`, available for `new_path` (a rename target names the file from then on). */
+int nerrf_trace_path_flags(const int64_t* off, const uint8_t* data, int64_t n, uint8_t* flags_out);
 int nerrf_trace_intern(int64_t n_events, const int64_t* order, const uint32_t* pid,
                        const int64_t* path_off, const uint8_t* path_data,
                        const int64_t* new_path_off, const uint8_t* new_path_data, int merge_renames,

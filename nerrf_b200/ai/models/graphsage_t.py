@@ -78,9 +78,14 @@ class GraphSAGE_T(nn.Module):
             self._node_b_cache = ((ver, self.node_b.data_ptr()), float(self.node_b.detach().cpu()))
         return self._node_b_cache[1]
 
-    @staticmethod
-    def _check_graph(x, rowptr, col, edge_w):
+    def _check_graph(self, x, rowptr, col, edge_w):
         L.require_cuda(x, rowptr, col, edge_w)
+        # raw pointers cross the C-ABI: a model left on the CPU or on another GPU would be a sticky illegal-address fault
+        if self.weights[0].device != x.device:
+            raise L.NerrfError(f"model parameters are on {self.weights[0].device}, inputs on {x.device}: call model.to(x.device)")
+        for t in (rowptr, col, edge_w):
+            if t.device != x.device:
+                raise L.NerrfError(f"graph tensors must share one device (got {t.device} and {x.device})")
         if x.dtype != torch.float32 or edge_w.dtype != torch.float32:
             raise TypeError("x and edge_w must be float32")
         if col.dtype != torch.int32:
@@ -125,12 +130,13 @@ class GraphSAGE_T(nn.Module):
             pp, npeers = L.ptr_array(peer_outs), len(peer_outs)
         else:
             pp, npeers = None, 0
-        L.check(L.lib().nerrf_sage_layer_fwd_ex(
-            L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
-            row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
-            L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
-            L.ptr(score_out), L.ptr(lws), lws_bytes, pp, npeers, L.ptr(peer_need), L.current_stream_ptr()),
-            "nerrf_sage_layer_fwd_ex")
+        with torch.cuda.device(h.device):
+            L.check(L.lib().nerrf_sage_layer_fwd_ex(
+                L.ptr(h), L.ptr(rowptr), int(rowptr.dtype == torch.int64), colp, ewp, L.ptr(W), L.ptr(b), L.ptr(out), N,
+                row_begin, row_end, h.shape[1], self.hidden, int(relu), algo_flags,
+                L.ptr(self.node_w) if score_out is not None else None, self._node_b_host() if score_out is not None else 0.0,
+                L.ptr(score_out), L.ptr(lws), lws_bytes, pp, npeers, L.ptr(peer_need), L.current_stream_ptr()),
+                "nerrf_sage_layer_fwd_ex")
         return out
 
     def _has_hub_rows(self, rowptr) -> bool:
@@ -187,11 +193,12 @@ class GraphSAGE_T(nn.Module):
         pp = ((N * self.hidden * 4 + 255) // 256) * 256 if self.num_layers > 1 else 0
         ws = torch.empty(pp + lbytes, device=dev, dtype=torch.uint8)
         Wp = L.ptr_array(list(self.weights)); bp = L.ptr_array(list(self.biases))
-        L.check(L.lib().nerrf_sage_forward(L.ptr(x), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col),
-                                           L.ptr(edge_w), N, self.in_dim, self.hidden, self.num_layers, Wp, bp,
-                                           L.ptr(self.node_w), self._node_b_host(), L.ptr(h), L.ptr(score), L.ptr(ws),
-                                           ws.numel(), ALGOS[self.algo],
-                                           L.current_stream_ptr()), "nerrf_sage_forward")
+        with torch.cuda.device(dev):
+            L.check(L.lib().nerrf_sage_forward(L.ptr(x), L.ptr(rowptr), int(rowptr.dtype == torch.int64), L.ptr(col),
+                                               L.ptr(edge_w), N, self.in_dim, self.hidden, self.num_layers, Wp, bp,
+                                               L.ptr(self.node_w), self._node_b_host(), L.ptr(h), L.ptr(score), L.ptr(ws),
+                                               ws.numel(), ALGOS[self.algo],
+                                               L.current_stream_ptr()), "nerrf_sage_forward")
         if return_edge_logits and self.edge_W is not None:
             _, el = self.heads(h, rowptr, col, return_edge_logits=True)
             return h, score, el

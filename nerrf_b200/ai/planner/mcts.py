@@ -155,6 +155,8 @@ class Plan:
     actions: list           # committed action indices, in order
     scores: list            # exact rewards.score after each commit (scores[0] = initial state)
     searches: list          # SearchResult per step
+    truncated: bool = False            # stopped at max_steps while an improving candidate still existed
+    remaining_candidates: int = 0      # improving single actions left when the plan stopped (0 = complete)
 
 
 def ranked_children(root_n, root_w):
@@ -175,7 +177,7 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
     exact reward improves on the current state is committed; the plan ends when none does."""
     A = actions.A
     state = RW.empty_state(A)
-    max_steps = depth if max_steps is None else max_steps
+    max_steps = A if max_steps is None else max_steps          # a plan may need every candidate; `depth` is the ROLLOUT horizon
     cur = float(RW.score(state[None, :], actions, device=device).cpu()[0])
     out = Plan([], [cur], [])
     ctx = SearchContext(actions, n_rollouts, depth, iterations, c, device)
@@ -194,4 +196,13 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
         k = int(better[0])
         state, cur = nxt[k].copy(), float(sc[k])
         out.actions.append(int(cand[k])); out.scores.append(cur)
+    if len(out.actions) >= max_steps and len(out.actions) < A:
+        # step limit hit: say so instead of handing back a silently incomplete plan (one batched exact-reward call)
+        rest = np.array([a for a in range(A) if not (state[a >> 5] >> np.uint32(a & 31)) & np.uint32(1)], np.int64)
+        if rest.size:
+            nxt = np.repeat(state[None, :], rest.size, axis=0)
+            nxt[np.arange(rest.size), rest >> 5] |= (np.uint32(1) << (rest & 31).astype(np.uint32)).astype(np.uint32)
+            sc = RW.score(nxt, actions, device=device).cpu().numpy()
+            out.remaining_candidates = int((sc > np.float32(cur)).sum())
+            out.truncated = out.remaining_candidates > 0
     return out

@@ -71,10 +71,15 @@ def roc_auc(scores, labels) -> float:
 # ------------------------------------------------------------------ toy set (simulator-schema LockBit traces)
 def make_example(seed: int, n_files: int = 30, benign_files: int = 40) -> dict:
     """One labelled example: a simulated LockBit trace -> graph tensors + per-file sequences.  Labels: a file node
-    is positive iff it was encrypted (graph.graph_from_events meta['label'])."""
+    is positive iff it was encrypted (graph.graph_from_events meta['label'], from the simulator's annotations).
+    Features are OBSERVABLE-ONLY (graph.OBSERVABLE_SLOT): the annotation event kinds that define the label
+    (file_encrypt_start / _complete, ...) are folded onto the syscalls the tracker can actually see
+    (openat / write / rename), so the gate below is not satisfied by reading the label back from the input.
+    What remains is what a wire trace carries: write / rename counts, byte counts, timing, the .lockbit extension
+    ("extension pattern", threat-model.mdx:178-184).  The toy set is still easy; see DESIGN.md 2.7."""
     ev = trace_sim.lockbit_trace(n_files=n_files, seed=seed, benign_files=benign_files)
-    g = G.graph_from_events(ev)
-    seq, lengths, nodes = pipeline.file_sequences(ev, g)
+    g = G.graph_from_events(ev, observable=True)
+    seq, lengths, nodes = pipeline.file_sequences(ev, g, observable=True)
     t = torch.from_numpy
     return {"x": t(g.x), "rowptr": t(g.rowptr), "col": t(g.col), "ew": t(g.ew),
             "label": t(g.meta["label"].astype(np.float32)), "is_file": t(g.meta["node_kind"] == 0),

@@ -212,10 +212,29 @@ extern "C" int nerrf_trace_decode(const uint8_t* buf, int64_t len, int64_t n_eve
     return NERRF_OK;
 }
 
+// NERRF_PATH_* bits of every string of a packed string column (same rules as the path_flags column of
+// nerrf_trace_decode); used for new_path, whose flags the decoder does not emit.
+extern "C" int nerrf_trace_path_flags(const int64_t* off, const uint8_t* data, int64_t n, uint8_t* flags_out) {
+    NERRF_REQUIRE(n >= 0 && off && flags_out && (data || n == 0 || off[n] == 0), "null pointer");
+    for (int64_t i = 0; i < n; ++i) {
+        NERRF_REQUIRE(off[i + 1] >= off[i], "offsets must be non-decreasing (string %lld)", (long long)i);
+        const uint8_t* s = data + off[i];
+        const uint64_t m = (uint64_t)(off[i + 1] - off[i]);
+        uint8_t pf = 0;
+        if (contains(s, m, ".lockbit", 8)) pf |= NERRF_PATH_LOCKBIT;
+        if (has_note_word(s, m)) pf |= NERRF_PATH_NOTE;
+        if (starts_with(s, m, "/tmp") || starts_with(s, m, "/proc")) pf |= NERRF_PATH_TMP;
+        if (ends_with(s, m, ".lockbit3")) pf |= NERRF_PATH_ENCRYPTED;
+        flags_out[i] = pf;
+    }
+    return NERRF_OK;
+}
+
 // Node interning in event order `order` (NULL = identity): one node per pid and one per file identity, ids in
 // order of first appearance over the interleaved (process, file[, rename target]) sequence -- exactly the numbering
 // of graph.py graph_from_events.  merge_renames: a file and its renamed / encrypted twin share the node (key = path
-// without its last extension) and new_path makes no node; else every distinct path is a node and a non-empty
+// without its last extension), a non-empty new_path ALIASES its own key to that node (and names it when it ends in
+// .lockbit3) instead of making a node; else every distinct path is a node and a non-empty
 // new_path gets one too (node_g, -1 when absent).
 extern "C" int nerrf_trace_intern(int64_t n_events, const int64_t* order, const uint32_t* pid, const int64_t* path_off,
                                   const uint8_t* path_data, const int64_t* new_path_off, const uint8_t* new_path_data,
@@ -259,6 +278,14 @@ extern "C" int nerrf_trace_intern(int64_t n_events, const int64_t* order, const 
         if (ends_with(s, n, ".lockbit3")) { node_name_event[fit->second] = i; node_name_which[fit->second] = 0; }   // rollback target
         node_g[i] = -1;
         const uint64_t gn = (uint64_t)(new_path_off[i + 1] - new_path_off[i]);
+        if (gn && merge_renames) {
+            // a real rename `a.dat -> a.dat.lockbit3`: the target is the same file identity whatever its stem (merge by
+            // inode); later events on the new name land on this node, and an encrypted target names the rollback
+            const uint8_t* g = new_path_data + new_path_off[i];
+            key.assign((const char*)g, stem_len(g, gn));
+            files.emplace(key, fit->second);                              // no-op when the key is already known
+            if (ends_with(g, gn, ".lockbit3")) { node_name_event[fit->second] = i; node_name_which[fit->second] = 1; }
+        }
         if (gn && !merge_renames) {
             key.assign((const char*)(new_path_data + new_path_off[i]), gn);
             auto git = files.find(key);

@@ -175,12 +175,38 @@ def events_from_event_batch(batch) -> list:
     return out
 
 
-def graph_from_events(events, merge_renames=True, window=None) -> TemporalGraph:
+# Observable-only event kinds: the simulator's annotations (file_created, file_encrypt_*, ransom_note_created) are
+# ground truth, not something the tracker can see -- it emits openat / write / rename only
+# (tracker/bpf/tracepoints.c:43-81).  `observable=True` folds every simulator kind onto the syscall it stands for,
+# so features built from simulator traces equal the features a wire-format trace of the same activity would give;
+# labels keep using the annotations.
+OBSERVABLE_SLOT = (4, 5, 6, 4, 4, 5, 6, 7)   # created->openat, encrypt_start->write, encrypt_complete->rename, note->openat
+
+
+def resolve_event_paths(events) -> list:
+    """Time-sorted copy of `events` in which every event names a file.  Real tracker traces carry no path on write
+    events (tracker/bpf/tracepoints.c:62-64 zeroes it): such an event is attributed to the most recent non-empty path
+    of the same pid (the file it has open, as far as the trace can tell); with no such path it identifies no file and is
+    dropped.  Without this every path-less event of every process would be interned as ONE file node named ''."""
+    evs = sorted(events, key=lambda e: _parse_ts(e["timestamp"]))     # lossy streams may be unordered
+    last: dict = {}
+    out = []
+    for e in evs:
+        if e.get("path"):
+            last[e["pid"]] = e["path"]
+            out.append(e)
+        elif e["pid"] in last:
+            d = dict(e); d["path"] = last[e["pid"]]; d["path_inferred"] = True
+            out.append(d)
+    return out
+
+
+def graph_from_events(events, merge_renames=True, window=None, observable=False) -> TemporalGraph:
     """Events -> temporal graph.  Nodes: one per pid (process) and one per file identity.
     Edges (both directions, so files aggregate from the process that touched them and the
     process from its files): process<->file per event with time t_e and conf_e = 1; rename /
     encrypt pairs are merged into one file node when merge_renames (else linked file<->file)."""
-    evs = sorted(events, key=lambda e: _parse_ts(e["timestamp"]))     # lossy streams may be unordered
+    evs = resolve_event_paths(events)
     if not evs:
         raise ValueError("empty trace")
     t0 = _parse_ts(evs[0]["timestamp"]); t1 = _parse_ts(evs[-1]["timestamp"])
@@ -209,6 +235,12 @@ def graph_from_events(events, merge_renames=True, window=None) -> TemporalGraph:
         src += [p, f]; dst += [f, p]; tt += [t, t]
         touched = [p, f]
         new_path = e.get("new_path") or ""
+        if new_path and merge_renames:
+            # a real rename `a.dat -> a.dat.lockbit3`: the target is the SAME file identity (merge by inode), whatever
+            # its stem; later events on the new name land on this node, and the encrypted name is the rollback target
+            node_id.setdefault(("f", _stem(new_path)), f)
+            if new_path.endswith(".lockbit3"):
+                names[f] = new_path
         if new_path and not merge_renames:
             g = nid(("f", new_path), 0, new_path)
             src += [f, g]; dst += [g, f]; tt += [t, t]
@@ -216,11 +248,12 @@ def graph_from_events(events, merge_renames=True, window=None) -> TemporalGraph:
         for n in touched:
             fv = feats.setdefault(n, {"cnt": np.zeros(_N_EVENT_SLOTS), "bytes": 0.0, "first": t, "last": t,
                                        "lockbit": 0.0, "note": 0.0, "tmp": 0.0})
-            fv["cnt"][_EVENT_SLOT.get(e["event"], _N_EVENT_SLOTS - 1)] += 1
+            slot = _EVENT_SLOT.get(e["event"], _N_EVENT_SLOTS - 1)
+            fv["cnt"][OBSERVABLE_SLOT[slot] if observable else slot] += 1
             fv["bytes"] += float(e.get("size", 0) or 0)
             fv["last"] = t
         fv = feats[f]
-        fv["lockbit"] = max(fv["lockbit"], 1.0 if ".lockbit" in path else 0.0)
+        fv["lockbit"] = max(fv["lockbit"], 1.0 if ".lockbit" in path or (merge_renames and ".lockbit" in new_path) else 0.0)
         fv["note"] = max(fv["note"], 1.0 if "README" in path.upper() or "RANSOM" in path.upper() else 0.0)
         fv["tmp"] = max(fv["tmp"], 1.0 if path.startswith("/tmp") or path.startswith("/proc") else 0.0)
         attacked = e["event"] in ATTACK_EVENTS or e.get("phase") == "attack" and e["event"].startswith("file_encrypt")
@@ -254,8 +287,10 @@ def graph_from_events(events, merge_renames=True, window=None) -> TemporalGraph:
         c = feats[n]["cnt"]
         k = max(c[0] + c[1] + c[2], 1.0)
         size_mb[n] = feats[n]["bytes"] / k / 1e6 if kinds[n] == 0 else 0.0
+    file_keys = {k[1]: v for k, v in node_id.items() if k[0] == "f"}      # merge key (or path) -> node, incl. rename aliases
     return TemporalGraph(rowptr, col, ew, x, {"kind": "trace", "names": names, "node_kind": np.asarray(kinds),
-                                              "label": y, "size_mb": size_mb, "t0": t0, "span": span})
+                                              "label": y, "size_mb": size_mb, "t0": t0, "span": span,
+                                              "file_keys": file_keys, "merge_renames": bool(merge_renames)})
 
 
 def graph_from_jsonl(path, **kw) -> TemporalGraph:

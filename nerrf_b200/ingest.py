@@ -83,6 +83,52 @@ def events_from_columns(cols: EventColumns) -> list:
              "pid": int(cols.pid[i]), "new_path": new_path[i]} for i in range(cols.n)]
 
 
+def _gather_strings(off, data, idx):
+    """Packed string column restricted / re-ordered to rows `idx` (vectorised variable-length gather)."""
+    ln = (off[idx + 1] - off[idx]).astype(np.int64)
+    new_off = np.zeros(idx.shape[0] + 1, np.int64)
+    np.cumsum(ln, out=new_off[1:])
+    total = int(new_off[-1])
+    if total == 0:
+        return new_off, np.zeros(0, np.uint8)
+    pos = np.arange(total, dtype=np.int64) - np.repeat(new_off[:-1], ln) + np.repeat(off[idx], ln)
+    return new_off, data[pos]
+
+
+def resolve_columns(cols: EventColumns) -> EventColumns:
+    """Columnar form of graph.resolve_event_paths: every event must name a file.  The tracker zeroes `path` on write
+    events (tracker/bpf/tracepoints.c:62-64); such an event takes the most recent non-empty path of the same pid
+    (in time order), or is dropped when there is none.  Returns `cols` itself when no path is empty."""
+    poff, pdata = cols.strings["path"]
+    empty = (poff[1:] - poff[:-1]) == 0
+    if cols.n == 0 or not empty.any():
+        return cols
+    order = np.argsort(cols.timestamp, kind="stable")
+    by_pid = order[np.argsort(cols.pid[order], kind="stable")]          # grouped by pid, time order inside a group
+    pid_g = cols.pid[by_pid]
+    start = np.r_[True, pid_g[1:] != pid_g[:-1]]
+    grp_first = np.maximum.accumulate(np.where(start, np.arange(cols.n), 0))
+    have = np.where(~empty[by_pid], np.arange(cols.n), -1)
+    last = np.maximum.accumulate(have)                                  # position of the last named event so far ...
+    ok = last >= grp_first                                              # ... if it belongs to the same pid
+    src = np.empty(cols.n, np.int64)                                    # event whose path this event uses, by stored index
+    src[by_pid] = np.where(ok, by_pid[np.maximum(last, 0)], -1)
+    keep = np.nonzero(src >= 0)[0]                                      # stored order is preserved for the survivors
+    strings = {name: _gather_strings(*cols.strings[name], keep) for name in STRING_COLUMNS if name != "path"}
+    strings["path"] = _gather_strings(poff, pdata, src[keep])
+    sc = {k: getattr(cols, k)[keep] for k in ("ts_sec", "ts_nanos", "pid", "tid", "flags", "ret_val", "bytes", "event_slot")}
+    return EventColumns(n=int(keep.shape[0]), path_flags=cols.path_flags[src[keep]], strings=strings, **sc)
+
+
+def path_flags_of(off, data) -> np.ndarray:
+    """NERRF_PATH_* bits of a packed string column (nerrf_trace_path_flags)."""
+    n = off.shape[0] - 1
+    out = np.zeros(max(n, 1), np.uint8)
+    d = data if data.size else np.zeros(1, np.uint8)
+    _lib.check(_lib.lib().nerrf_trace_path_flags(_p(off), _p(d), n, _p(out)), "nerrf_trace_path_flags")
+    return out[:n]
+
+
 def intern_nodes(cols: EventColumns, order=None, merge_renames=True):
     """-> node_p, node_f, node_g (int32 [n], by stored event index; node_g = -1 when absent), kind int8 [N],
     name_event int64 [N], name_which int8 [N]."""
@@ -116,12 +162,13 @@ def _node_names(cols, name_event, name_which):
             for v, w in enumerate(name_which.tolist())]
 
 
-def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, device=None) -> G.TemporalGraph:
+def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, device=None, observable=False) -> G.TemporalGraph:
     """Same graph as graph.graph_from_events(events_from_columns(cols)) -- nodes, numbering, CSR, weights, features,
     labels -- without a per-event Python loop.  device=None: arrays are numpy (host stages).  device="cuda[:i]":
     the per-node features (graph.node_features_device) and the edge sort / CSR / temporal weights
     (graph.build_csr_device) run on the GPU; rowptr, col, ew, x are CUDA tensors ready for GraphSAGE_T.forward
     (rowptr / col / labels identical to the host path, ew and x within the rounding of exp / log1p)."""
+    cols = resolve_columns(cols)                              # path-less (write) events follow the pid's open file
     n = cols.n
     if n == 0:
         raise ValueError("empty trace")
@@ -134,9 +181,12 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     N = kind.shape[0]
     P = node_p[order].astype(np.int64); F = node_f[order].astype(np.int64); Gn = node_g[order].astype(np.int64)
     t = ts[order] - t0
-    slot = cols.event_slot[order].astype(np.int64)
+    raw_slot = cols.event_slot[order].astype(np.int64)
+    slot = np.asarray(G.OBSERVABLE_SLOT, np.int64)[raw_slot] if observable else raw_slot
     size = cols.bytes[order].astype(np.float64)
     pf = cols.path_flags[order]
+    if merge_renames:                                         # the renamed twin is this node: its .lockbit bit counts
+        pf = pf | (path_flags_of(*cols.strings["new_path"])[order] & np.uint8(1))
     has_g = Gn >= 0
 
     # edges, in the per-event order of the host loader: p->f, f->p [, f->g, g->f]
@@ -147,7 +197,8 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     conf = np.ones(src.shape[0], np.float32)
 
     names = _node_names(cols, name_event, name_which)
-    meta = {"kind": "trace", "names": names, "node_kind": kind.astype(np.int64), "t0": t0, "span": span}
+    meta = {"kind": "trace", "names": names, "node_kind": kind.astype(np.int64), "t0": t0, "span": span,
+            "merge_renames": bool(merge_renames)}
     if device is not None:
         # device path: features by integer atomics + one node pass, edges sorted into CSR by the radix-sort stage
         import torch
@@ -158,7 +209,10 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
                                                    up(pf, np.uint8), up(kind, np.int8), window)
         rowptr, col, ew = G.build_csr_device(up(src, np.int32), up(dst, np.int32), up(tt, np.float32), up(conf, np.float32), N,
                                              t_ref=float(span), tau=G.TAU)
-        meta.update(label=label.cpu().numpy().astype(np.int64), size_mb=size_mb.cpu().numpy(), device=str(dev))
+        lab = label.cpu().numpy().astype(np.int64)
+        if observable:                                        # the kernel saw the folded slots: labels come from the annotations
+            lab = (np.bincount(F[(raw_slot == 1) | (raw_slot == 2)], minlength=N) > 0).astype(np.int64)
+        meta.update(label=lab, size_mb=size_mb.cpu().numpy(), device=str(dev))
         return G.TemporalGraph(rowptr, col, ew, x, meta)
 
     # per-node features over the touched nodes (p, f [, g]) of every event
@@ -170,7 +224,7 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     np.minimum.at(first, tn, ttime); np.maximum.at(last, tn, ttime)
     flag = lambda bit: (np.bincount(F[(pf & bit) != 0], minlength=N) > 0).astype(np.float64)
     lockbit, note, tmp = flag(1), flag(2), flag(4)
-    label = (np.bincount(F[(slot == 1) | (slot == 2)], minlength=N) > 0).astype(np.int64)
+    label = (np.bincount(F[(raw_slot == 1) | (raw_slot == 2)], minlength=N) > 0).astype(np.int64)
 
     indeg = np.bincount(dst, minlength=N).astype(np.float32)
     outdeg = np.bincount(src, minlength=N).astype(np.float32)
@@ -192,12 +246,13 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     return G.TemporalGraph(rowptr, col, ew, x, meta)
 
 
-def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None):
+def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, observable=False):
     """Per-file event sequences for the LSTM without per-event Python: the same arrays as
     pipeline.file_sequences(events_from_columns(cols), graph) -- seq fp32 [n_files, t_max, 16], lengths int32, node ids --
     (the last t_max events of every file node, oldest first; feature layout: pipeline.file_sequences)."""
     from .ai.models import lstm
     t_max = t_max or lstm.T_MAX
+    cols = resolve_columns(cols)
     n = cols.n
     ts = cols.timestamp
     order = np.argsort(ts, kind="stable")
@@ -219,6 +274,8 @@ def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None):
     seq = np.zeros((nodes.size, t_max, lstm.D_IN), np.float32)
     lengths = np.minimum(count, t_max).astype(np.int32)
     slot = cols.event_slot[order][ev].astype(np.int64)
+    if observable:
+        slot = np.asarray(G.OBSERVABLE_SLOT, np.int64)[slot]
     seq[row, k, slot] = 1.0
     seq[row, k, 8] = np.log1p(cols.bytes[order][ev].astype(np.float64)) / 20.0
     prev_t = np.empty(n); prev_t[1:] = tt[by_file][:-1]; prev_t[0] = 0.0

@@ -24,19 +24,22 @@ _SEQ_EVENT_SLOT = {"file_created": 0, "file_encrypt_start": 1, "file_encrypt_com
                    "openat": 4, "write": 5, "rename": 6}
 
 
-def file_sequences(events, g: G.TemporalGraph, t_max=lstm.T_MAX):
+def file_sequences(events, g: G.TemporalGraph, t_max=lstm.T_MAX, observable=False):
     """Per-file event sequences for the LSTM (the last `t_max` events of each file node, oldest first).
     Features (D_in = 16): one-hot event kind (8), log1p(size)/20, dt to the previous event of the file (s, clipped),
     time since trace start / window, .lockbit flag, /tmp|/proc flag, 3 spare (the simulator's `phase` annotation is
     ground truth, not an observable: it is deliberately NOT a feature, so wire-format traces give the same sequences)."""
-    names = {n: i for i, n in enumerate(g.meta["names"])}
-    stem_of = {G._stem(n): i for n, i in names.items()}
-    evs = sorted(events, key=lambda e: G._parse_ts(e["timestamp"]))
+    merge = g.meta.get("merge_renames", True)
+    keys = g.meta.get("file_keys")
+    if keys is None:                                       # graphs from the columnar constructor: rebuild the key map from the names
+        keys = {(G._stem(n) if merge else n): i for i, n in enumerate(g.meta["names"])}
+    key_of = (lambda p_: G._stem(p_)) if merge else (lambda p_: p_)
+    evs = G.resolve_event_paths(events)                    # path-less (write) events follow the pid's open file
     t0 = G._parse_ts(evs[0]["timestamp"]) if evs else 0.0
     span = max(G._parse_ts(evs[-1]["timestamp"]) - t0, 1e-6) if evs else 1.0
     per_file: dict = {}
     for e in evs:
-        node = stem_of.get(G._stem(e["path"]))
+        node = keys.get(key_of(e["path"]))
         if node is None or g.meta["node_kind"][node] != 0:
             continue
         per_file.setdefault(node, []).append(e)
@@ -49,7 +52,8 @@ def file_sequences(events, g: G.TemporalGraph, t_max=lstm.T_MAX):
         prev = None
         for k, e in enumerate(es):
             t = G._parse_ts(e["timestamp"])
-            seq[i, k, _SEQ_EVENT_SLOT.get(e["event"], 7)] = 1.0
+            slot = _SEQ_EVENT_SLOT.get(e["event"], 7)
+            seq[i, k, G.OBSERVABLE_SLOT[slot] if observable else slot] = 1.0
             seq[i, k, 8] = np.log1p(float(e.get("size", 0) or 0)) / 20.0
             seq[i, k, 9] = min(t - prev, 10.0) if prev is not None else 0.0
             seq[i, k, 10] = (t - t0) / span
@@ -107,7 +111,7 @@ def run(g: G.TemporalGraph, seq, lengths, seq_nodes, model: GraphSAGE_T, seq_mod
         actions = Actions(p, size_mb, np.ones(a, np.float32))
     else:
         actions = Actions.from_scores(score[candidates], probs[:, 0], size_mb, np.zeros(a, np.int64))
-    pl = mcts.plan(actions, max_steps=plan_steps if plan_steps is not None else depth, n_rollouts=n_rollouts, depth=depth,
+    pl = mcts.plan(actions, max_steps=plan_steps, n_rollouts=n_rollouts, depth=depth,
                    iterations=iterations, device=dev)
     sync(); tm["mcts_plan"] = (time.perf_counter() - t0) * 1e3
     tm["total"] = sum(tm.values())

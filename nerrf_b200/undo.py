@@ -28,13 +28,13 @@ def load_trace(path: str, device="cuda"):
     """-> (graph, seq, lengths, seq_nodes, n_events)"""
     if path.endswith(".jsonl") or path.endswith(".json"):
         events = G.read_trace_jsonl(path)
-        g = G.graph_from_events(events)
-        seq, lengths, nodes = pipeline.file_sequences(events, g)
+        g = G.graph_from_events(events, observable=True)          # the features ai/train.py trains on
+        seq, lengths, nodes = pipeline.file_sequences(events, g, observable=True)
         return g, seq, lengths, nodes, len(events)
     with open(path, "rb") as f:
         cols = ingest.decode_event_batch(f.read())
-    g = ingest.graph_from_columns(cols, device=device)
-    seq, lengths, nodes = ingest.sequences_from_columns(cols)
+    g = ingest.graph_from_columns(cols, device=device, observable=True)
+    seq, lengths, nodes = ingest.sequences_from_columns(cols, observable=True)
     return g, seq, lengths, nodes, cols.n
 
 
@@ -62,6 +62,9 @@ def main(argv=None) -> dict:
     ap.add_argument("--out", default=None, help="plan JSON (default: stdout)"); ap.add_argument("--shell", default=None)
     ap.add_argument("--top-a", type=int, default=1024); ap.add_argument("--rollouts", type=int, default=1024)
     ap.add_argument("--depth", type=int, default=50); ap.add_argument("--iterations", type=int, default=16)
+    ap.add_argument("--max-steps", type=int, default=None,
+                    help="cap on the number of reversions (default: every candidate may be reverted); a capped plan that "
+                         "leaves improving candidates is marked truncated and is not auto-approvable")
     ap.add_argument("--device", default="cuda")
     a = ap.parse_args(argv)
     if not torch.cuda.is_available():
@@ -73,7 +76,7 @@ def main(argv=None) -> dict:
     model, scorer = load_models(a.weights, a.train_epochs, log=log)
     model.to(a.device); scorer.to(a.device)
     res = pipeline.run(g, seq, lengths, nodes, model, scorer, top_a=min(a.top_a, 4096), n_rollouts=a.rollouts, depth=a.depth,
-                       iterations=a.iterations, plan_steps=max(a.depth, 1), device=a.device)
+                       iterations=a.iterations, plan_steps=a.max_steps, device=a.device)
     plan = emit.from_pipeline(g, res, attack_id=a.id)
     plan["stats"] = {"events": int(n_events), "nodes": int(g.num_nodes), "edges": int(g.num_edges),
                      "candidates": int(len(res.candidates)), "ingest_ms": t_ingest,

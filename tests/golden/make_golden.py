@@ -53,6 +53,11 @@ def main():
             gg = G.graph_from_jsonl(f"{ref}/{name}/results/{name}_trace.jsonl")
             enc = sorted(l.split()[-1] for l in open(f"{ref}/{name}/results/file_list.txt") if ".lockbit3" in l)
             names = gg.meta["names"]
+            # the same trace with OBSERVABLE features only (simulator annotations folded onto openat/write/rename):
+            # what ai/train.py trains on and what a wire-format trace of the same activity would give
+            go = G.graph_from_jsonl(f"{ref}/{name}/results/{name}_trace.jsonl", observable=True)
+            assert np.array_equal(go.rowptr, gg.rowptr) and np.array_equal(go.col, gg.col)
+            tr[f"{name}_x_obs"] = go.x
             tr.update({f"{name}_rowptr": gg.rowptr, f"{name}_col": gg.col, f"{name}_ew": gg.ew, f"{name}_x": gg.x,
                        f"{name}_label": gg.meta["label"], f"{name}_kind": gg.meta["node_kind"],
                        f"{name}_size_mb": gg.meta["size_mb"],

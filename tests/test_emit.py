@@ -50,3 +50,33 @@ def test_partial_scores_and_numpy_ids():
     plan = emit.undo_plan(["/f0.lockbit3", "/f1"], np.asarray([1, 0]), scores=[-3.0, -2.0])
     assert plan["steps"][0]["op"] == "restore_snapshot" and plan["steps"][0]["reward_after"] == -2.0
     assert "reward_after" not in plan["steps"][1] and plan["reward_after"] == -2.0
+
+
+def test_hostile_names_cannot_inject_commands(tmp_path):
+    """a newline in a path used to end the `# restore ...` comment line and start a command."""
+    marker = tmp_path / "PWNED"
+    names = {0: f"/data/a\ntouch {marker} #.dat", 1: f"/data/b'; touch {marker}; '.dat", 2: f"/data/$(touch {marker}).dat",
+             3: f"/data/`touch {marker}`\r.dat"}
+    plan = emit.undo_plan(names, [0, 1, 2, 3])
+    assert all(s["op"] == "restore_snapshot" for s in plan["steps"])
+    assert plan["steps"][0]["hostile_name"] and plan["steps"][3]["hostile_name"] and "hostile_name" not in plan["steps"][1]
+    script = emit.to_shell(plan)
+    assert not any(l.lstrip().startswith("#") for l in script.splitlines()[1:])      # no comment lines carry data
+    subprocess.run(["sh", "-c", script], cwd=tmp_path, check=True)
+    assert not marker.exists()
+    # a rename of a hostile encrypted name: the file is moved, nothing else happens
+    enc = "we ird\n$(touch PWNED)'name.lockbit3"                                   # cwd = tmp_path: same marker file
+    (tmp_path / enc).write_text("x")
+    plan = emit.undo_plan({0: enc}, [0])
+    subprocess.run(["sh", "-c", emit.to_shell(plan)], cwd=tmp_path, check=True)
+    assert (tmp_path / (enc[:-len(".lockbit3")] + ".dat")).exists() and not marker.exists()
+    assert json.loads(emit.to_json(plan))["steps"][0]["from"] == enc                 # exact bytes survive the JSON form
+
+
+def test_empty_path_is_refused_and_truncation_is_reported():
+    import pytest
+    with pytest.raises(ValueError):
+        emit.reversion_for("")
+    plan = emit.undo_plan(["/a.lockbit3"], [0], truncated=True, remaining_candidates=7)
+    assert plan["truncated"] and plan["remaining_candidates"] == 7 and plan["approve_if"] != "all_checks_pass"
+    assert emit.undo_plan(["/a.lockbit3"], [0])["approve_if"] == "all_checks_pass"

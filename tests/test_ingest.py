@@ -177,3 +177,71 @@ def test_columnar_sequences_equal_per_event_sequences():
     seq, lengths, nodes = ingest.sequences_from_columns(cols)
     assert np.array_equal(nodes, want_nodes) and np.array_equal(lengths, want_len) and lengths.max() == 100
     assert np.array_equal(seq.view(np.uint32), want_seq.view(np.uint32)), np.argwhere(seq != want_seq)[:5]
+
+
+def _tracker_style_events():
+    """What the real tracker emits (tracker/bpf/tracepoints.c:43-81): openat with a path, write WITHOUT a path, rename
+    with path + new_path; two processes interleaved; one write before any open (it can name no file)."""
+    ev, t = [], 1_700_000_000.0
+    def emit(pid, syscall, path="", new_path="", size=0):
+        nonlocal t
+        t += 0.125
+        ev.append({"timestamp": t, "event": syscall, "path": path, "new_path": new_path, "size": size, "pid": pid})
+    emit(9, "write", size=77)                                        # no open yet: dropped
+    for i in range(4):
+        emit(7, "openat", f"/data/doc{i}.dat")
+        emit(8, "openat", f"/srv/log{i}.txt")
+        emit(7, "write", size=4096 + i)                              # -> /data/doc{i}.dat
+        emit(8, "write", size=100 + i)                               # -> /srv/log{i}.txt
+        emit(7, "write", size=4096)
+        emit(7, "rename", f"/data/doc{i}.dat", f"/data/doc{i}.dat.lockbit3")
+    emit(7, "openat", "/data/doc0.dat.lockbit3")                     # later event on the NEW name: same node
+    return ev
+
+
+@pytest.mark.parametrize("merge", [True, False])
+def test_tracker_style_trace_pathless_writes_and_real_renames(merge):
+    """path-less write events must not be interned as one global '' file node, and a real rename
+    a.dat -> a.dat.lockbit3 must keep the identity and yield the rollback name."""
+    ev = _tracker_style_events()
+    wire = ingest.encode_event_batch(ev)
+    cols = ingest.decode_event_batch(wire)
+    assert cols.n == len(ev)
+    want = G.graph_from_events(ingest.events_from_columns(cols), merge_renames=merge)
+    got = ingest.graph_from_columns(cols, merge_renames=merge)
+    _graphs_equal(got, want)
+    names = got.meta["names"]
+    assert "" not in names and "pid:9" not in names                 # the unattributable write is gone, with its process
+    if merge:
+        assert sorted(n for n in names if n.startswith("/data")) == [f"/data/doc{i}.dat.lockbit3" for i in range(4)]
+        assert len(names) == 2 + 4 + 4                              # 2 pids, 4 docs (twin merged), 4 logs
+        doc0 = names.index("/data/doc0.dat.lockbit3")
+        assert got.x[doc0, 16] == 1.0                               # .lockbit bit from the rename target
+        assert got.x[doc0, 5 + 5] == np.float32(np.log1p(2.0))      # both path-less writes were attributed to it
+        assert got.x[doc0, 5 + 4] == np.float32(np.log1p(2.0))      # open of the old AND of the new name
+        from nerrf_b200.ai.planner import emit
+        assert emit.reversion_for(names[doc0]) == {"op": "rename", "from": "/data/doc0.dat.lockbit3", "to": "/data/doc0.dat.dat"}
+    else:
+        assert "/data/doc0.dat" in names and "/data/doc0.dat.lockbit3" in names
+    # sequences: columnar == per-event, and every sequence belongs to a real file node
+    from nerrf_b200 import pipeline
+    w_seq, w_len, w_nodes = pipeline.file_sequences(ingest.events_from_columns(cols), want)
+    seq, lengths, nodes = ingest.sequences_from_columns(cols, merge_renames=merge)
+    assert np.array_equal(nodes, w_nodes) and np.array_equal(lengths, w_len)
+    assert np.array_equal(seq.view(np.uint32), w_seq.view(np.uint32))
+    assert all(got.meta["node_kind"][n] == 0 for n in nodes)
+
+
+def test_observable_mode_hides_the_simulator_annotations():
+    """features must not contain the ground-truth event kinds the label is defined by."""
+    ev = trace_sim.lockbit_trace(n_files=8, seed=2, benign_files=6)
+    g = G.graph_from_events(ev, observable=True)
+    assert not g.x[:, 5:9].any()                                     # slots 0..3 (simulator-only kinds) are never counted
+    assert g.meta["label"].sum() == 8                                # labels still come from the annotations
+    gc = ingest.graph_from_columns(ingest.decode_event_batch(ingest.encode_event_batch(ev)), observable=True)
+    assert np.array_equal(gc.x.view(np.uint32), g.x.view(np.uint32)) and np.array_equal(gc.meta["label"], g.meta["label"])
+    from nerrf_b200 import pipeline
+    seq, _, _ = pipeline.file_sequences(ev, g, observable=True)
+    assert not seq[:, :, 0:4].any()
+    seq2, _, _ = ingest.sequences_from_columns(ingest.decode_event_batch(ingest.encode_event_batch(ev)), observable=True)
+    assert np.array_equal(seq2[:, :, :8], seq[:, :, :8])

@@ -59,10 +59,17 @@ def test_m2_gate_on_the_reference_traces(trained, name):
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_m1_graph.npz"))
     t = torch.from_numpy
     with torch.no_grad():
-        logit = T.sage_node_logits(model, t(z[name + "_x"]), t(z[name + "_rowptr"]), t(z[name + "_col"]), t(z[name + "_ew"]))
+        logit = T.sage_node_logits(model, t(z[name + "_x_obs"]), t(z[name + "_rowptr"]), t(z[name + "_col"]), t(z[name + "_ew"]))
     files = z[name + "_kind"] == 0
     auc = T.roc_auc(logit.numpy()[files], z[name + "_label"][files])
     assert auc >= 0.90, auc
+
+
+def test_training_features_carry_no_annotation_slots():
+    """the label-defining event kinds are not features (graph.OBSERVABLE_SLOT)."""
+    ex = T.make_example(5, n_files=6, benign_files=5)
+    assert not ex["x"][:, 5:9].any() and not ex["seq"][:, :, 0:4].any()
+    assert ex["label"].sum() == 6
 
 
 def test_checkpoint_round_trip_into_the_undo_cli_loader(tmp_path):
