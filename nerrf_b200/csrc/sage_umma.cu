@@ -19,14 +19,18 @@
 // memory B operand.  Warp roles in one CTA per SM (512 threads):
 //   warps 0-3   epilogue: tcgen05.ld accumulator (lane = feature), + bias, ReLU, 128 B/warp stores
 //   warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma, commit -> mbarriers)
-//   warp  5     edge-block loader: stages each tile's rowptr / col / ew slice into shared memory with
-//               cp.async (completion on an mbarrier), running up to IDX_STAGES tiles ahead; the next tile's
-//               rowptr words are prefetched before it waits for a free stage
-//   warps 6-15  gather: one CSR row per warp at a time (sage_gather.cuh), rows round-robin; indices
-//               come from shared memory, so the only global latency a row exposes is its x rows
+//   warp  5     edge-block loader: stages each tile's rowptr words and its col / ew slices into shared memory --
+//               the slices as two BULK async copies (cp.async.bulk, byte count on the stage's mbarrier) --
+//               running up to IDX_STAGES tiles ahead; the next tile's rowptr words are prefetched before it
+//               waits for a free stage
+//   warps 6-..  gather: one CSR row per warp at a time, rows round-robin; every source row (512 B at F=128,
+//               128 B at F=32) is ONE bulk async copy into the warp's shared-memory ring, completion counted in
+//               bytes on the ring slot's mbarrier (the "TMA-staged edge block" of the north star); indices come
+//               from shared memory, so the only global latency a row exposes is its x rows
 // Pipelines: idx stages full/empty (loader <-> gather), smem operand stages full/empty (gather <-> MMA),
 // TMEM accumulators full/empty (MMA <-> epilogue).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sage_gather.cuh"
 
@@ -41,7 +45,8 @@ constexpr int MMA_WARP = 4;
 constexpr int LOADER_WARP = 5;
 constexpr int GATHER_WARP0 = 6;
 constexpr int EMAX = 512;              // staged edges per tile (4 KB); the rest of a heavier tile is read from global
-constexpr int IDX_STAGE_BYTES = EMAX * 8 + 512;      // col[EMAX] | ew[EMAX] | rp[TN+1] (relative) | e_lo (int64)
+constexpr int EPAD = EMAX + 4;         // a slice is copied as its 16-byte aligned superset: up to 3 leading + 3 trailing elements
+constexpr int IDX_STAGE_BYTES = EPAD * 8 + 512;      // col[EPAD] | ew[EPAD] | rp[TN+1] (relative) | e_lo (int64) | col_off, ew_off
 // items (source rows) per sub-batch (= one cp.async group): 4 warp-wide copy instructions, i.e. 4 * (32 / (F/4))
 template <int F> constexpr int qs_for() { return 4 * (32 / (F / 4)); }
 constexpr int NQ = 4;                  // sub-batch slots in a warp's ring; NQ-1 groups are in flight
@@ -66,7 +71,7 @@ struct UmmaCfg {
     static constexpr int ACC_COL0 = NS * W_PART_COLS;
     static constexpr int TMEM_COLS = (ACC_COL0 + 2 * TN <= 256) ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + IDX_STAGES * IDX_STAGE_BYTES +
-                                   (size_t)GATHER_WARPS * RING_BYTES + 1024 /*head reduce*/ + 1024 /*align*/ + 256 /*barriers*/;
+                                   (size_t)GATHER_WARPS * RING_BYTES + 1024 /*head reduce*/ + 1024 /*align*/ + 1024 /*barriers*/;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least two smem stages");
     static_assert(ACC_COL0 + 2 * TN <= 512, "TMEM overflow");
@@ -80,6 +85,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// arrive (count 1) and add `bytes` to the phase's pending transaction count: the phase completes when the
+// arrival count AND the byte count are both satisfied
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bulk async copy global -> shared (the non-tensor TMA path, SASS UBLKCP): `bytes` (multiple of 16) from a 16-byte
+// aligned global address to a 16-byte aligned shared address; completion is signalled on `bar` as complete_tx(bytes)
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -124,13 +141,6 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (does not add to the pending count)
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -378,7 +388,12 @@ __global__ void __launch_bounds__(256) long_chunk_kernel(const float* __restrict
 
 // LONG: compiled with the hub-row (pre-aggregated partial items) paths; the plain variant is used when the
 // launch has no hub-row scratch, so graphs without hub rows pay nothing for the feature.
-template <int F, int NS, typename RP, bool LONG>
+// BULK: source rows travel as one bulk async copy each (cp.async.bulk, SASS UBLKCP) instead of 32 lanes x 16-byte
+// cp.async (LDGSTS).  Measured on B200 (profiles/r02_gather_transport.md): the TMA unit retires ~one bulk request per
+// 20-30 cycles per SM, so at one request per 128..512-byte row it -- not HBM, not issue slots -- becomes the limiter
+// (F=128 layer 1.24 ms vs 1.01 ms).  The LDGSTS transport is therefore the default; the edge-block slices (col / ew,
+// kilobytes per request) use bulk copies in both variants.
+template <int F, int NS, typename RP, bool LONG, bool BULK>
 __global__ void __launch_bounds__((UmmaCfg<F, NS>::THREADS), 1)
 sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
@@ -400,8 +415,11 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     auto idxf_bar = [&](int q) { return bar_base + 8u * (2 * C::STAGES + 4 + q); };
     auto idxe_bar = [&](int q) { return bar_base + 8u * (2 * C::STAGES + 4 + IDX_STAGES + q); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4 + 2 * IDX_STAGES);
+    // per gather warp: NQ ring-slot barriers (bulk-copy byte counts), private to the warp
+    auto ring_bar = [&](int g, int q) { return bar_base + 256u + 8u * (uint32_t)(g * NQ + q); };
+    static_assert(256 + GATHER_WARPS * NQ * 8 <= 1024, "barrier area");
     unsigned char* idx_gen = smem_gen + (idx_base - smem_base);
-    const uint32_t ring_base = bar_base + 256;
+    const uint32_t ring_base = bar_base + 1024;
     float* head_red = reinterpret_cast<float*>(smem_gen + (ring_base - smem_base) + (size_t)GATHER_WARPS * C::RING_BYTES);   // [2][4][32]
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -413,8 +431,11 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         if (lane == 0) {
             for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), TN); mbar_init(empty_bar(s), 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), EPI_WARPS * 32); }
-            // idx full: 32 async (cp.async) arrivals + 1 release-arrive for the rowptr words; empty: one per gather warp
-            for (int q = 0; q < IDX_STAGES; ++q) { mbar_init(idxf_bar(q), 33); mbar_init(idxe_bar(q), GATHER_WARPS); }
+            // idx full: ONE arrive.expect_tx by the loader (publishes the rowptr words, counts the bytes of the two bulk
+            // copies); empty: one per gather warp.  ring slots: one arrive.expect_tx by the issuing lane per use
+            for (int q = 0; q < IDX_STAGES; ++q) { mbar_init(idxf_bar(q), 1); mbar_init(idxe_bar(q), GATHER_WARPS); }
+            for (int g = 0; g < GATHER_WARPS; ++g)
+                for (int q = 0; q < NQ; ++q) mbar_init(ring_bar(g, q), 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -454,18 +475,21 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     if (warp >= GATHER_WARP0) {
         // =========================================================== gather warps (producers of the B operand)
         // Row stream of this warp: i = g, g+G, g+2G, ... over the CTA's tiles.  A row is the item list
-        // [self, edge_0 .. edge_{deg-1}], cut into sub-batches of QS items.  Every sub-batch is one cp.async
-        // group that lands QS source rows in a slot of this warp's shared-memory ring; NQ-1 groups stay in
-        // flight while the oldest is consumed (LDS + FFMA), so memory-level parallelism is bounded by the
-        // ring, not by registers, and no load ever stalls a scoreboard.
-        constexpr int G = 32 / LPR;                                     // items fetched by one warp instruction
+        // [self, edge_0 .. edge_{deg-1}], cut into sub-batches of QS items.  Every item is ONE bulk async copy of a
+        // whole source row (F*4 bytes) into a slot of this warp's shared-memory ring, issued by the lane that owns
+        // the item; the slot's mbarrier counts the bytes.  NQ-1 sub-batches stay in flight while the oldest is
+        // consumed (LDS + FFMA), so memory-level parallelism is bounded by the ring, not by registers, no load ever
+        // stalls a scoreboard, and a source row costs one copy instruction instead of one per 16 bytes.
+        constexpr int G = 32 / LPR;                                     // items consumed by one warp-wide LDS.128
         constexpr int QS = C::QS;
         constexpr int SLOT_FLOATS = QS * F;
+        constexpr uint32_t ROW_BYTES = F * 4;
         const int g = warp - GATHER_WARP0;
         const int grp = lane / LPR, sub = lane % LPR;
-        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES) + (uint32_t)((grp * F + 4 * sub) * 4);
-        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_base - smem_base) + (size_t)g * C::RING_BYTES) + grp * F + 4 * sub;
+        // LDGSTS transport: lane (grp, sub) moves bytes [16 sub, 16 sub + 16) of item t + grp; bulk: whole rows
+        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES) + (BULK ? 0u : (uint32_t)((grp * F + 4 * sub) * 4));
         const float* xs = x + 4 * sub;
+        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_base - smem_base) + (size_t)g * C::RING_BYTES) + grp * F + 4 * sub;
         const int tiles_mine = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles in this CTA's sequence
         const int stream_end = tiles_mine * TN;
 
@@ -483,9 +507,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 itl = tl;
             }
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
-            icol = reinterpret_cast<const int32_t*>(ibp);
-            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EMAX * 8);
-            ielo = *reinterpret_cast<const int64_t*>(ibp + EMAX * 8 + 384);
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
+            icol = reinterpret_cast<const int32_t*>(ibp) + rp_s[96 + 2];            // + alignment offset of the col slice
+            ielo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
             const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
             ib = 0; inb = 1; ideg = -1;
             if (row < row_end) {
@@ -505,9 +529,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             const int tl = ci / TN, r = ci % TN;
             ctl = tl;
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
-            cew = reinterpret_cast<const float*>(ibp + EMAX * 4);
-            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EMAX * 8);
-            celo = *reinterpret_cast<const int64_t*>(ibp + EMAX * 8 + 384);
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
+            cew = reinterpret_cast<const float*>(ibp + EPAD * 4) + rp_s[96 + 3];    // + alignment offset of the ew slice
+            celo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
             const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
             cb = 0; cnb = 1; cdeg = -1;
             if (row < row_end) {
@@ -522,8 +546,8 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 cnb = (citems + QS - 1) / QS;
             }
         };
-        // one cp.async group = sub-batch `ib` of the issue row, into ring slot `slot`
-        auto issue = [&](int slot) {
+        // LDGSTS transport: one cp.async group = sub-batch `ib` of the issue row, into ring slot `slot`
+        auto issue_ldgsts = [&](int slot) {
             if (ii < stream_end) {
                 if (ideg >= 0) {
                     const int first = ib * QS;
@@ -568,6 +592,36 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             }
             cp_async_commit();                                            // (possibly empty) group keeps the count in step
         };
+        // sub-batch `ib` of the issue row -> ring slot `slot`: lane j < nitems copies item j (one bulk copy per source row)
+        auto issue_bulk = [&](int slot) {
+            const uint32_t bar = ring_bar(g, slot);
+            uint32_t tx = 0;
+            if (ii < stream_end) {
+                if (ideg >= 0) {
+                    const int first = ib * QS;
+                    int nitems = iitems - first;                         // items left in the row (>= 1)
+                    nitems = nitems < QS ? nitems : QS;
+                    tx = (uint32_t)nitems * ROW_BYTES;
+                    if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+                    if (lane < nitems) {
+                        const int it = first + lane;                     // item number inside the row; 0 = the self row
+                        const int k = ie0 + it - 1;                      // its edge, relative to the staged slice
+                        const float* srcp;
+                        if (it == 0) srcp = x + (size_t)irow * F;
+                        else if (LONG && ilong >= 0) srcp = lw.partial + (size_t)(ilong + it - 1) * 128;   // pre-aggregated chunk
+                        else srcp = x + (size_t)(uint32_t)((k < EMAX) ? icol[k] : __ldg(col + ielo + k)) * F;
+                        bulk_g2s(ring_u32 + (uint32_t)((slot * QS + lane) * (int)ROW_BYTES), srcp, ROW_BYTES, bar);
+                    }
+                }
+                if (++ib >= inb) {
+                    ii += GATHER_WARPS;
+                    if (ii < stream_end) setup_issue_row();
+                }
+            }
+            if (tx == 0 && lane == 0) mbar_arrive(bar);                   // empty sub-batch: keeps the slot's phase in step
+        };
+
+        auto issue = [&](int slot) { if constexpr (BULK) issue_bulk(slot); else issue_ldgsts(slot); };
 
         if (ii < stream_end) { setup_issue_row(); }
         if (ci < stream_end) { setup_consume_row(); }
@@ -577,10 +631,16 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), self = acc;
         float wsum = 0.f;
         int last_tl = -1;
+        uint32_t ring_phase = 0;                                          // bit q = parity to wait for on ring slot q
         while (ci < stream_end) {
-            cp_async_wait<NQ - 2>();                                      // oldest group landed (this lane's part) ...
-            __syncwarp();                                                 // ... and everyone else's; also: all lanes are
-                                                                          // done reading the slot consumed last iteration
+            if constexpr (BULK) {
+                mbar_wait(ring_bar(g, cslot), (ring_phase >> cslot) & 1u);    // oldest sub-batch landed (all its bytes)
+                ring_phase ^= 1u << cslot;
+            } else {
+                cp_async_wait<NQ - 2>();                                  // oldest group landed (this lane's part) ...
+            }
+            __syncwarp();                                                 // ... and everyone else's;                                                 // all lanes are done reading the slot consumed
+                                                                          // last iteration
             issue(islot);                                                 // refill that slot
             islot = (islot + 1) % NQ;
             if (cdeg >= 0) {
@@ -676,7 +736,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             ci += GATHER_WARPS;
             if (ci < stream_end) setup_consume_row();
         }
-        cp_async_wait<0>();
+        if constexpr (!BULK) cp_async_wait<0>();
     } else if (warp == LOADER_WARP) {
         // =========================================================== edge-block loader
         constexpr int RPW = (TN + 1 + 31) / 32;
@@ -701,20 +761,31 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             const int64_t e_lo = __shfl_sync(0xffffffffu, rp[0], 0);
             const int64_t e_hi = __shfl_sync(0xffffffffu, rp[TN / 32], TN % 32);
             unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
-            int32_t* rp_s = reinterpret_cast<int32_t*>(ib + EMAX * 8);
+            int32_t* rp_s = reinterpret_cast<int32_t*>(ib + EPAD * 8);
 #pragma unroll
             for (int k = 0; k < RPW; ++k)
                 if (lane + 32 * k <= TN) rp_s[lane + 32 * k] = (int32_t)(rp[k] - e_lo);
-            if (lane == 0) *reinterpret_cast<int64_t*>(ib + EMAX * 8 + 384) = e_lo;
             const int n = (int)((e_hi - e_lo) < EMAX ? (e_hi - e_lo) : EMAX);
-            const uint32_t cs = idx_base + (uint32_t)(q * IDX_STAGE_BYTES), ws = cs + EMAX * 4;
-            for (int k = lane; k < n; k += 32) {
-                cp_async4(cs + 4u * k, col + e_lo + k);
-                cp_async4(ws + 4u * k, ew + e_lo + k);
+            // the col / ew slices [e_lo, e_lo + n) as the 16-byte aligned supersets bulk copies need: the slice starts
+            // `off` elements into its staged array (the gather warps add it); an over-read stays inside the 16-byte
+            // line that holds the first / last element
+            const uintptr_t ca = reinterpret_cast<uintptr_t>(col + e_lo), wa = reinterpret_cast<uintptr_t>(ew + e_lo);
+            const uint32_t c_off = (uint32_t)(ca & 15u) >> 2, w_off = (uint32_t)(wa & 15u) >> 2;
+            const uint32_t c_bytes = n ? (((uint32_t)n + c_off) * 4u + 15u) & ~15u : 0u;
+            const uint32_t w_bytes = n ? (((uint32_t)n + w_off) * 4u + 15u) & ~15u : 0u;
+            if (lane == 0) {
+                *reinterpret_cast<int64_t*>(ib + EPAD * 8 + 384) = e_lo;
+                rp_s[96 + 2] = (int32_t)c_off; rp_s[96 + 3] = (int32_t)w_off;
             }
-            cp_async_mbar_arrive_noinc(idxf_bar(q));                     // fires when this lane's copies have landed
-            __syncwarp();
-            if (lane == 0) mbar_arrive(idxf_bar(q));                     // release: publishes the rowptr words
+            __syncwarp();                                                // every lane's rowptr words are written ...
+            if (lane == 0) {
+                const uint32_t cs = idx_base + (uint32_t)(q * IDX_STAGE_BYTES), ws = cs + EPAD * 4;
+                mbar_arrive_expect_tx(idxf_bar(q), c_bytes + w_bytes);   // ... and published by this release-arrive
+                if (n) {
+                    bulk_g2s(cs, reinterpret_cast<const void*>(ca & ~(uintptr_t)15), c_bytes, idxf_bar(q));
+                    bulk_g2s(ws, reinterpret_cast<const void*>(wa & ~(uintptr_t)15), w_bytes, idxf_bar(q));
+                }
+            }
 #pragma unroll
             for (int k = 0; k < RPW; ++k) rp[k] = rp_next[k];
         }
@@ -837,6 +908,14 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     }
 }
 
+// the per-row bulk-copy transport is an experiment knob (NERRF_SAGE_ROW_COPY=bulk), compiled for the headline shapes only
+template <int F, int NS, typename RP>
+constexpr bool kBulkVariant = (NS == 3) && (F == 32 || F == 128) && (sizeof(RP) == 4);
+inline bool bulk_rows_requested() {
+    static const bool v = [] { const char* e = getenv("NERRF_SAGE_ROW_COPY"); return e && e[0] == 'b'; }();
+    return v;
+}
+
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
@@ -847,8 +926,10 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
     cudaGetDevice(&dev_);
     bool& attr_set = attr_set_dev[dev_ & 63];          // function attributes are per device
     if (!attr_set) {
-        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        if constexpr (kBulkVariant<F, NS, RP>)
+            NERRF_CHECK_CUDA(cudaFuncSetAttribute(sage_layer_umma_kernel<F, NS, RP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_set = true;
     }
     const int64_t rows = row_end - row_begin;
@@ -869,10 +950,15 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
         if (rc) return rc;
     }
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+    // the per-row bulk-copy transport needs 16-byte aligned rows; every transport stages col / ew with bulk copies,
+    // which only need 4-byte aligned slices (the aligned superset is copied)
     if (lw.cap > 0)
-        sage_layer_umma_kernel<F, NS, RP, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
-    else
-        sage_layer_umma_kernel<F, NS, RP, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+        sage_layer_umma_kernel<F, NS, RP, true, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+    else if (kBulkVariant<F, NS, RP> && bulk_rows_requested() && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if constexpr (kBulkVariant<F, NS, RP>)
+            sage_layer_umma_kernel<F, NS, RP, false, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+    } else
+        sage_layer_umma_kernel<F, NS, RP, false, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
     return launch_status("sage_layer_umma_kernel");
 }
 

@@ -180,16 +180,27 @@ def root_parallel_search(search_fn, rank, world, group=None):
 
 
 # ----------------------------------------------------------------------------------------------- GPU side
-def gpu_synthetic_graph(N, E, seed, device, relabel=False):
+def gpu_synthetic_graph(N, E, seed, device, relabel=False, family="hub_src"):
     """relabel=True applies a random vertex relabeling (an isomorphic graph): the hub nodes, which every shard
     references, are then spread evenly over the row blocks instead of all living in rank 0's block -- the usual
     partitioning pre-step that balances the per-rank exchange volume.
     Same distribution as graph.synthetic_graph (dst ~ U, src = floor(N u^3), t ~ U[0,60), conf ~ U[.5,1]),
     generated on the GPU so every rank can build the N x 10M-edge graph in about a second.  The CUDA Philox
-    generator is deterministic per (seed, call order), so all ranks hold the same graph."""
+    generator is deterministic per (seed, call order), so all ranks hold the same graph.
+    family: "hub_src" (the headline generator), "hub_dst" (roles swapped: rows with 10^4..10^5 in-edges, SURVEY.md 8d's
+    stress variant) or "uniform" (src and dst uniform: no hub rows for the L2 to hold)."""
     gen = torch.Generator(device=device).manual_seed(seed)
-    dst = torch.randint(0, N, (E,), generator=gen, device=device, dtype=torch.int64)
-    src = (N * torch.rand(E, generator=gen, device=device, dtype=torch.float64) ** 3).long().clamp_(max=N - 1)
+    uni = torch.randint(0, N, (E,), generator=gen, device=device, dtype=torch.int64)
+    skew = (N * torch.rand(E, generator=gen, device=device, dtype=torch.float64) ** 3).long().clamp_(max=N - 1)
+    if family == "hub_src":
+        dst, src = uni, skew
+    elif family == "hub_dst":
+        dst, src = skew, uni
+    elif family == "uniform":
+        dst, src = uni, torch.randint(0, N, (E,), generator=gen, device=device, dtype=torch.int64)
+    else:
+        raise ValueError(f"unknown graph family {family!r}")
+    del uni, skew
     t = torch.rand(E, generator=gen, device=device) * G.WINDOW
     conf = 0.5 + 0.5 * torch.rand(E, generator=gen, device=device)
     if relabel:
