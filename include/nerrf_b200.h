@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERRF_ABI_VERSION 1
+#define NERRF_ABI_VERSION 2   /* 2: guard arrays (planner spec v1), MCTS host session, nerrf_trace_path_flags */
 
 #define NERRF_OK 0
 #define NERRF_ERR_INVALID (-1)   /* bad argument (shape, alignment, unsupported size)      */
@@ -136,28 +136,42 @@ int nerrf_sage_session_destroy(nerrf_sage_session* s);
 /* ------------------------------------------------------------------ rewards.score (row a6)
  * Replaces: ai/planner/rewards.py (README.md:74,115 `Reward = -(data_loss + 0.1*downtime)`;
  * threat-model.mdx:205-223).  states uint32 [B, n_words], n_words = 32*NW, NW = 1/2/4 for
- * A <= 1024/2048/4096; action a = bit (a&31) of word (a>>5).  Bit-exact fixed-order fp32. */
+ * A <= 1024/2048/4096; action a = bit (a&31) of word (a>>5).  Bit-exact fixed-order fp32.
+ * guard (device int32 [A], or NULL): planner spec v1 -- guard[a] = index (0..31) of the "kill process" action
+ * (threat-model.mdx:212-215) that makes reverting a durable, or -1; an applied action whose guard is NOT applied
+ * additionally loses p_guard * p_a * size_a (the live process re-encrypts the file).  NULL = spec v0. */
 int nerrf_reward_score(const uint32_t* states, int64_t B, const float* p, const float* size,
-                       const float* cost, int A, float* out, nerrf_stream_t stream);
+                       const float* cost, const int32_t* guard, int A, float* out, nerrf_stream_t stream);
 
 /* ------------------------------------------------------------------ planner.mcts.search (a5)
  * Replaces: ai/planner/mcts.py (README.md:74, ROADMAP.md:84; architecture.mdx:62-72).
- * Leaf-parallel UCT, one persistent cooperative kernel for all T iterations.
- * Workspace layout is private; query its size first.  Outputs: root_n int32 [A_pad],
+ * Leaf-parallel UCT, one persistent cooperative kernel for all T iterations, ONE grid barrier per
+ * iteration (every CTA keeps its own replica of the tree).
+ * Workspace layout is private (it grows with the SM count); query its size first.  Outputs: root_n int32 [A_pad],
  * root_w fp32 [A_pad] (A_pad = 1024*NW), num_nodes int32 [1] -- all device pointers.
  * ln_table: device fp32 [T+2], ln_table[k] = fp32(ln(k*R)).  R must be a power of two. */
 int nerrf_mcts_workspace_bytes(int A, int T, int R, size_t* bytes);
-int nerrf_mcts_search(const float* p, const float* size, const float* cost, int A,
+int nerrf_mcts_search(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
                       const uint32_t* root_state, int R, int D, int T, uint64_t seed, float c,
                       float lo, float inv_range, const float* ln_table, int32_t* root_n,
                       float* root_w, int32_t* num_nodes, void* workspace, size_t workspace_bytes,
                       nerrf_stream_t stream);
-/* HOST in / HOST out convenience (allocates + frees device memory internally, synchronous).
- * root_state_host may be NULL.  Also returns the tree arrays' root rows only. */
-int nerrf_mcts_search_host(const float* p, const float* size, const float* cost, int A,
+/* HOST in / HOST out, one-shot (allocates + frees device memory internally, synchronous).
+ * root_state_host and guard may be NULL. */
+int nerrf_mcts_search_host(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
                            const uint32_t* root_state_host, int R, int D, int T, uint64_t seed,
                            float c, float lo, float inv_range, const float* ln_table_host,
                            int32_t* root_n_host, float* root_w_host, int32_t* num_nodes_host);
+/* HOST in / HOST out through a session: the device buffers and a stream live in the handle (create once for the
+ * largest A / T / R; a search is then six small H2D copies, one launch and three D2H copies, no allocation).
+ * A must have the same word count NW as A_max. */
+typedef struct nerrf_mcts_session nerrf_mcts_session;
+int nerrf_mcts_session_create(int A_max, int T_max, int R_max, nerrf_mcts_session** out);
+int nerrf_mcts_session_search_host(nerrf_mcts_session* s, const float* p, const float* size, const float* cost,
+                                   const int32_t* guard, int A, const uint32_t* root_state_host, int R, int D, int T,
+                                   uint64_t seed, float c, float lo, float inv_range, const float* ln_table_host,
+                                   int32_t* root_n_host, float* root_w_host, int32_t* num_nodes_host);
+int nerrf_mcts_session_destroy(nerrf_mcts_session* s);
 
 /* ------------------------------------------------------------------ lstm.forward (row a4)
  * Replaces: ai/models/lstm.py (README.md:73; architecture.mdx:55-59; threat-model.mdx:191-203).

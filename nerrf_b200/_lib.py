@@ -40,12 +40,16 @@ SIGNATURES = {
     "nerrf_sage_session_set_weights": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_float]),
     "nerrf_sage_session_forward_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int]),
     "nerrf_sage_session_destroy": (C.c_int, [vp]),
-    "nerrf_reward_score": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int, vp, vp]),
+    "nerrf_reward_score": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, C.c_int, vp, vp]),
     "nerrf_mcts_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
-    "nerrf_mcts_search": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float,
+    "nerrf_mcts_search": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float,
                                     C.c_float, C.c_float, vp, vp, vp, vp, vp, C.c_size_t, vp]),
-    "nerrf_mcts_search_host": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float,
+    "nerrf_mcts_search_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float,
                                          C.c_float, C.c_float, vp, vp, vp, vp]),
+    "nerrf_mcts_session_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "nerrf_mcts_session_search_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                                 C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]),
+    "nerrf_mcts_session_destroy": (C.c_int, [vp]),
     "nerrf_lstm_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "nerrf_lstm_forward": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp),
                                      C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, C.c_size_t, vp]),
@@ -81,7 +85,7 @@ def lib():
         fn = getattr(h, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if h.nerrf_abi_version() != 1:
+    if h.nerrf_abi_version() != 2:
         raise NerrfError("ABI version mismatch between nerrf_b200/_lib.py and libnerrf_b200.so")
     _lib = h
     return h

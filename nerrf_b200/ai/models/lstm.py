@@ -92,6 +92,13 @@ class LSTMScorer(nn.Module):
 
 Model = LSTMScorer
 
+
+def default_algo() -> str:
+    """Which kernel family nerrf_lstm_forward runs: the tcgen05 path unless NERRF_LSTM_ALGO=ffma selects the fp32
+    CUDA-core kernel (kept as an independent cross-check)."""
+    import os
+    return "ffma" if os.environ.get("NERRF_LSTM_ALGO", "").lower().startswith("f") else "umma (tcgen05)"
+
 _default = None
 
 

@@ -81,6 +81,7 @@ class SearchContext:
         _, _, self.A_pad, self.nw = RW.layout(A)
         with torch.cuda.device(self.device):
             self.p, self.size, self.cost = actions.device_arrays(self.device)
+            self.guard = actions.device_guard(self.device)
             self.d_ln = torch.from_numpy(ln_table(self.T, self.R)).to(self.device)
             self.d_root = torch.empty(self.nw, device=self.device, dtype=torch.int32)
             # root_n | root_w | num_nodes in one buffer -> one D2H
@@ -100,7 +101,7 @@ class SearchContext:
         self.h_root.copy_(torch.from_numpy(root.view(np.int32)))
         self.d_root.copy_(self.h_root, non_blocking=True)
         o = self.d_out
-        L.check(L.lib().nerrf_mcts_search(L.ptr(self.p), L.ptr(self.size), L.ptr(self.cost), A, L.ptr(self.d_root), self.R,
+        L.check(L.lib().nerrf_mcts_search(L.ptr(self.p), L.ptr(self.size), L.ptr(self.cost), L.ptr(self.guard), A, L.ptr(self.d_root), self.R,
                                           self.D if depth is None else int(depth), self.T, C.c_uint64(seed), self.c,
                                           float(lo), float(inv), L.ptr(self.d_ln), C.c_void_p(o.data_ptr()),
                                           C.c_void_p(o.data_ptr() + 4 * self.A_pad), C.c_void_p(o.data_ptr() + 8 * self.A_pad),
@@ -121,12 +122,36 @@ class SearchContext:
             return self.fetch(lo, inv)
 
 
+class HostSession:
+    """Host-buffer search handle (include/nerrf_b200.h nerrf_mcts_session_*): device buffers and a stream are allocated
+    once; pass it as `host_call=` to search()."""
+
+    def __init__(self, max_actions=1024, max_iterations=64, max_rollouts=4096, device=None):
+        self.handle = C.c_void_p()
+        dev = torch.device(device or "cuda")
+        with torch.cuda.device(dev):
+            L.check(L.lib().nerrf_mcts_session_create(int(max_actions), int(max_iterations), int(max_rollouts), C.byref(self.handle)),
+                    "nerrf_mcts_session_create")
+
+    def close(self):
+        if self.handle:
+            L.lib().nerrf_mcts_session_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def search(actions: Actions, scorer=None, n_rollouts: int = 4096, depth: int = 50, seed: int = 0,
            c: float = math.sqrt(2.0), iterations: int = 64, root_state=None, device=None, host_call: bool = False,
            context: SearchContext | None = None) -> SearchResult:
     """One tree search.  `scorer` must be None or ai.planner.rewards.score: the reward is evaluated
     inside the kernel (batched, R states per iteration).  host_call=True goes through the
-    host-buffer C-ABI entry (copies inside the call).  Pass a SearchContext to reuse device buffers."""
+    host-buffer C-ABI entry (copies inside the call; a HostSession instead of True reuses its device buffers).
+    Pass a SearchContext to reuse device buffers on the device-pointer path."""
     if scorer is not None and scorer is not RW.score:
         raise NotImplementedError("the CUDA planner evaluates ai.planner.rewards.score in-kernel; "
                                   "custom scorers are not supported")
@@ -141,9 +166,16 @@ def search(actions: Actions, scorer=None, n_rollouts: int = 4096, depth: int = 5
         lnN = ln_table(T, R)
         root_n = np.zeros(A_pad, np.int32); root_w = np.zeros(A_pad, np.float32); nn = np.zeros(1, np.int32)
         as_p = lambda a: a.ctypes.data_as(C.c_void_p)
-        L.check(L.lib().nerrf_mcts_search_host(as_p(actions.p), as_p(actions.size), as_p(actions.cost), A, as_p(root), R, D, T,
-                                               C.c_uint64(seed), float(c), float(lo), float(inv), as_p(lnN), as_p(root_n),
-                                               as_p(root_w), as_p(nn)), "nerrf_mcts_search_host")
+        gp = as_p(actions.guard) if actions.guard is not None else None
+        if isinstance(host_call, HostSession):
+            L.check(L.lib().nerrf_mcts_session_search_host(host_call.handle, as_p(actions.p), as_p(actions.size), as_p(actions.cost), gp,
+                                                           A, as_p(root), R, D, T, C.c_uint64(seed), float(c), float(lo), float(inv),
+                                                           as_p(lnN), as_p(root_n), as_p(root_w), as_p(nn)),
+                    "nerrf_mcts_session_search_host")
+        else:
+            L.check(L.lib().nerrf_mcts_search_host(as_p(actions.p), as_p(actions.size), as_p(actions.cost), gp, A, as_p(root), R, D, T,
+                                                   C.c_uint64(seed), float(c), float(lo), float(inv), as_p(lnN), as_p(root_n),
+                                                   as_p(root_w), as_p(nn)), "nerrf_mcts_search_host")
         return SearchResult(root_n[:A].copy(), root_w[:A].copy(), best_child(root_n[:A], root_w[:A]), int(nn[0]),
                             float(lo), float(inv), R * T)
     ctx = context or SearchContext(actions, R, D, T, c, device)
@@ -169,33 +201,71 @@ def ranked_children(root_n, root_w):
 
 
 def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096, depth: int = 50, seed: int = 0,
-         c: float = math.sqrt(2.0), iterations: int = 64, device=None) -> Plan:
+         c: float = math.sqrt(2.0), iterations: int = 64, device=None, commit_per_search: int = 1, merge=None,
+         lookahead: bool | None = None, patience: int = 8) -> Plan:
     """Undo plan = repeated search / commit / re-root.  Each step the search ranks the root
     children; the candidates are then VALIDATED with the exact reward (one batched
     rewards.score call over all candidate next-states, mirroring the reference's "sandbox
     validates, then apply" gate, architecture.mdx:81-86): the highest-ranked candidate whose
-    exact reward improves on the current state is committed; the plan ends when none does."""
+    exact reward improves on the current state is committed; the plan ends when none does.
+
+    commit_per_search > 1: after a search, up to that many ranked candidates are committed, each one re-validated
+    with the exact reward against the state INCLUDING the commits before it (large incidents: thousands of files
+    would otherwise need one tree search per file).
+    merge: root parallelism over several GPUs -- a callable (root_n, root_w) -> (root_n, root_w) that sums the root
+    statistics of all ranks in rank order (nerrf_b200.dist); every rank then takes identical decisions.
+    lookahead (default: on when the actions carry guards, spec v1): the reward is then not separable -- killing a process
+    costs downtime and only pays off through the reversions it makes durable -- so a step that no single action improves
+    is not the end: the search's recommended child is committed TENTATIVELY, planning continues from there for at most
+    `patience` steps below the best reward seen, and the plan is finally cut back to its best prefix (what the sandbox
+    would approve)."""
     A = actions.A
     state = RW.empty_state(A)
     max_steps = A if max_steps is None else max_steps          # a plan may need every candidate; `depth` is the ROLLOUT horizon
     cur = float(RW.score(state[None, :], actions, device=device).cpu()[0])
     out = Plan([], [cur], [])
     ctx = SearchContext(actions, n_rollouts, depth, iterations, c, device)
-    for step in range(max_steps):
-        res = ctx.search(seed + step, state, depth=max(depth - step, 1))
+    step = 0
+    lookahead = (actions.guard is not None) if lookahead is None else lookahead
+    best_score, best_len = cur, 0
+    while len(out.actions) < max_steps:
+        # one-commit-per-search plans keep a total horizon of `depth` moves; batch-committing plans (large incidents)
+        # search with the full rollout horizon every time
+        res = ctx.search(seed + step, state, depth=max(depth - len(out.actions), 1) if commit_per_search == 1 else depth)
+        step += 1
+        if merge is not None:
+            n, w = merge(res.root_n, res.root_w)
+            res = SearchResult(n, w, best_child(n, w), res.num_nodes, res.lo, res.inv_range, res.rollouts)
         out.searches.append(res)
         cand = ranked_children(res.root_n, res.root_w)
         if cand.size == 0:
             break
-        nxt = np.repeat(state[None, :], cand.size, axis=0)
-        nxt[np.arange(cand.size), cand >> 5] |= (np.uint32(1) << (cand & 31).astype(np.uint32)).astype(np.uint32)
-        sc = RW.score(nxt, actions, device=device).cpu().numpy()
-        better = np.nonzero(sc > np.float32(cur))[0]
-        if better.size == 0:
+        committed = 0
+        while cand.size and committed < commit_per_search and len(out.actions) < max_steps:
+            nxt = np.repeat(state[None, :], cand.size, axis=0)
+            nxt[np.arange(cand.size), cand >> 5] |= (np.uint32(1) << (cand & 31).astype(np.uint32)).astype(np.uint32)
+            sc = RW.score(nxt, actions, device=device).cpu().numpy()
+            better = np.nonzero(sc > np.float32(cur))[0]
+            if better.size == 0:
+                if lookahead and committed == 0 and len(out.actions) - best_len < patience:
+                    better = np.zeros(1, np.int64)                       # tentative: the search's recommendation
+                else:
+                    break
+            k = int(better[0])
+            state, cur = nxt[k].copy(), float(sc[k])
+            out.actions.append(int(cand[k])); out.scores.append(cur)
+            committed += 1
+            if cur > best_score:
+                best_score, best_len = cur, len(out.actions)
+            cand = cand[better[1:]] if commit_per_search > 1 else cand[:0]     # only candidates that still looked improving
+        if committed == 0 or (lookahead and len(out.actions) - best_len >= patience):
             break
-        k = int(better[0])
-        state, cur = nxt[k].copy(), float(sc[k])
-        out.actions.append(int(cand[k])); out.scores.append(cur)
+    if len(out.actions) > best_len:                                      # drop a tentative tail that never paid off
+        out.actions = out.actions[:best_len]; out.scores = out.scores[:best_len + 1]
+        state = RW.empty_state(A)
+        for a_ in out.actions:
+            state[a_ >> 5] |= np.uint32(1) << np.uint32(a_ & 31)
+        cur = best_score
     if len(out.actions) >= max_steps and len(out.actions) < A:
         # step limit hit: say so instead of handing back a silently incomplete plan (one batched exact-reward call)
         rest = np.array([a for a in range(A) if not (state[a >> 5] >> np.uint32(a & 31)) & np.uint32(1)], np.int64)

@@ -8,6 +8,11 @@ effects" (docs/content/docs/architecture.mdx:71); candidate cost/confidence exam
     data_loss(s) = sum_{a not in s} p_a size_a + sum_{a in s} (1-p_a) size_a ;  downtime(s) = sum_{a in s} cost_a
     score(s) = -(data_loss + 0.1 downtime)            fp32, fixed association order (bit-exact)
 
+Spec v1 adds the one non-separable term the reference's own candidate list implies
+(threat-model.mdx:208-222: "Reverse file encryption" next to "Kill process python3"): every action may name a GUARD
+-- the index (< 32) of the "kill process" action of the process that wrote its file.  An applied action whose guard
+is NOT applied additionally loses w_a = p_guard * p_a * size_a: the live process re-encrypts the reverted file.
+
 States are bitsets: uint32 [B, n_words], action a = bit (a & 31) of word (a >> 5),
 n_words = 32*NW with NW = 1/2/4 for A <= 1024/2048/4096.
 """
@@ -34,6 +39,7 @@ class Actions:
     cost: np.ndarray
     kind: np.ndarray | None = None
     names: list = field(default_factory=list)
+    guard: np.ndarray | None = None      # int32 [A]: index (< 32) of the kill action guarding a, or -1 (spec v1)
 
     def __post_init__(self):
         self.p = np.ascontiguousarray(_np(self.p), dtype=np.float32)
@@ -43,6 +49,11 @@ class Actions:
             raise ValueError("p, size, cost must be 1-D arrays of equal length")
         if not 1 <= self.p.shape[0] <= 4096:
             raise ValueError("number of actions must be in 1..4096")
+        if self.guard is not None:
+            g = np.ascontiguousarray(_np(self.guard), dtype=np.int32)
+            if g.shape != self.p.shape or (g < -1).any() or (g >= 32).any() or (g >= self.p.shape[0]).any():
+                raise ValueError("guard must be -1 or the index (< 32, < A) of the kill action, one per action")
+            self.guard = g if (g >= 0).any() else None
 
     @property
     def A(self):
@@ -58,6 +69,9 @@ class Actions:
 
     def device_arrays(self, device):
         return tuple(torch.from_numpy(a).to(device) for a in (self.p, self.size, self.cost))
+
+    def device_guard(self, device):
+        return None if self.guard is None else torch.from_numpy(self.guard).to(device)
 
 
 def _np(a):
@@ -113,9 +127,11 @@ def score(states, actions: Actions, device=None) -> torch.Tensor:
     st = st.contiguous().view(-1, nw)
     B = st.shape[0]
     p, size, cost = actions.device_arrays(device)
+    guard = actions.device_guard(device)
     out = torch.empty(B, device=device, dtype=torch.float32)
-    L.check(L.lib().nerrf_reward_score(L.ptr(st), B, L.ptr(p), L.ptr(size), L.ptr(cost), actions.A, L.ptr(out),
-                                       L.current_stream_ptr()), "nerrf_reward_score")
+    with torch.cuda.device(device):
+        L.check(L.lib().nerrf_reward_score(L.ptr(st), B, L.ptr(p), L.ptr(size), L.ptr(cost), L.ptr(guard), actions.A, L.ptr(out),
+                                           L.current_stream_ptr()), "nerrf_reward_score")
     return out
 
 
@@ -128,12 +144,19 @@ def reward_bounds(actions: Actions, root_state=None):
     u = (p * actions.size).astype(np.float32).astype(np.float64)
     v = ((one - p).astype(np.float32) * actions.size).astype(np.float32).astype(np.float64)
     applied_cost = v + 0.1 * actions.cost.astype(np.float64)
+    applied_worst = applied_cost
+    if actions.guard is not None:            # an applied action may also pay its guard penalty: a valid (not tight) bound
+        g = actions.guard.astype(np.int64)
+        u32 = (p * actions.size).astype(np.float32); v32 = ((one - p).astype(np.float32) * actions.size).astype(np.float32)
+        w32 = (np.where(g >= 0, p[np.maximum(g, 0)], np.float32(0.0)).astype(np.float32) * u32).astype(np.float32)
+        vw = np.where(g >= 0, (v32 + w32).astype(np.float32), v32).astype(np.float64)
+        applied_worst = vw + 0.1 * actions.cost.astype(np.float64)
     fixed = np.zeros(A, bool)
     if root_state is not None:
         rs = np.asarray(root_state, np.uint32)
         idx = np.arange(A)
         fixed = ((rs[idx >> 5] >> (idx & 31).astype(np.uint32)) & np.uint32(1)) != 0
-    worst = np.where(fixed, applied_cost, np.maximum(u, applied_cost))
+    worst = np.where(fixed, applied_worst, np.maximum(u, applied_worst))
     best = np.where(fixed, applied_cost, np.minimum(u, applied_cost))
     lo = np.float32(-math.fsum(worst.tolist()))
     hi = -math.fsum(best.tolist())

@@ -14,7 +14,7 @@ namespace nerrf {
 
 // tensor-core path (lstm_umma.cu), selected with NERRF_LSTM_ALGO=umma
 bool lstm_umma_enabled();
-size_t lstm_umma_workspace_bytes(int64_t B, int T);
+size_t lstm_umma_workspace_bytes(int64_t B, int T, int num_layers);
 int lstm_layers_umma(const float* seq, const int32_t* len, int64_t B, int T, int D_in, int num_layers, const float* const* Wih_t,
                      const float* const* Whh_t, const float* const* bias, float* hfin, void* workspace, size_t workspace_bytes,
                      cudaStream_t st);
@@ -165,7 +165,7 @@ extern "C" int nerrf_lstm_workspace_bytes(int64_t B, int T, int H, size_t* bytes
     NERRF_REQUIRE(bytes, "null out");
     NERRF_REQUIRE(B >= 0 && T >= 1 && H == LH, "LSTM: need B >= 0, T >= 1, H == 256");
     *bytes = ((size_t)2 * B * T * 2 * H + (size_t)B * 2 * H) * sizeof(float) + 256;
-    if (lstm_umma_enabled() && B > 0) *bytes = lstm_umma_workspace_bytes(B, T) + (size_t)B * 2 * H * sizeof(float) + 512;
+    if (lstm_umma_enabled() && B > 0) *bytes = lstm_umma_workspace_bytes(B, T, 2) + (size_t)B * 2 * H * sizeof(float) + 512;
     return NERRF_OK;
 }
 

@@ -13,10 +13,14 @@
 //            sum over its 32*NW actions (terms staged in smem, transposed -> conflict-free)
 //            + xor-butterfly; value written to val[r]
 //   grid barrier (monotonic counter: one atomicAdd + ld.acquire spin per CTA; co-residency is guaranteed by
-//                 the cooperative launch; cheaper than cg::grid.sync with one fat CTA per SM)
-//   backup   CTA 0: adjacent-pairs tree sum of val -> path edges; all CTAs: per-first-action
-//            child statistics of the leaf (fixed ascending-r order)
-//   grid barrier
+//                 the cooperative launch; cheaper than cg::grid.sync with one fat CTA per SM) -- the ONLY one per
+//                 iteration: every CTA keeps its own replica of the tree and applies the (deterministic) backup to it
+//                 redundantly from the shared rollout values, so no CTA ever waits for another CTA's tree writes;
+//                 val[] is double buffered across iterations
+//   backup   every CTA, on its replica: adjacent-pairs tree sum of val -> path edges; per-first-action child
+//            statistics of the leaf (fixed ascending-r order)
+// Reward spec v1 (oracle/rewards_ref.py): an applied action whose GUARD (a "kill process" action, index < 32, i.e. a
+// bit of state word 0) is not applied contributes vw_a = fl(v_a + fl(p_g * u_a)) instead of v_a.
 #include "common.cuh"
 
 namespace nerrf {
@@ -40,28 +44,45 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Stage u/v/cost into smem, transposed: action a = lane*chunk + i lives at [i*32 + lane].
+// Stage u / v / vw / cost (+ guard index) into smem, transposed: action a = lane*chunk + i lives at [i*32 + lane].
+struct TermsS { float *u, *v, *vw, *c; uint8_t* g; };
+template <int NW>
+__device__ __forceinline__ TermsS carve_terms(unsigned char* smem) {
+    constexpr int A_PAD = 1024 * NW;
+    TermsS t;
+    t.u = reinterpret_cast<float*>(smem); t.v = t.u + A_PAD; t.vw = t.v + A_PAD; t.c = t.vw + A_PAD;
+    t.g = reinterpret_cast<uint8_t*>(t.c + A_PAD);
+    return t;
+}
+template <int NW>
+constexpr size_t terms_smem_bytes() { return (size_t)1024 * NW * (4 * 4 + 1); }
+
 template <int NW>
 __device__ __forceinline__ void stage_terms(const float* __restrict__ p, const float* __restrict__ size,
-                                            const float* __restrict__ cost, int A, float* u_s, float* v_s, float* c_s) {
+                                            const float* __restrict__ cost, const int32_t* __restrict__ guard, int A, TermsS t) {
     constexpr int CHUNK = 32 * NW, A_PAD = 1024 * NW;
     for (int a = threadIdx.x; a < A_PAD; a += blockDim.x) {
-        float u = 0.f, v = 0.f, c = 0.f;
+        float u = 0.f, v = 0.f, vw = 0.f, c = 0.f;
+        int g = 255;
         if (a < A) {
             const float pa = p[a], sa = size[a];
             u = __fmul_rn(pa, sa);
             v = __fmul_rn(__fsub_rn(1.0f, pa), sa);
             c = cost[a];
+            vw = v;
+            const int gd = guard ? guard[a] : -1;
+            if (gd >= 0 && gd < 32 && gd < A) { g = gd; vw = __fadd_rn(v, __fmul_rn(p[gd], u)); }
         }
         const int lane = a / CHUNK, i = a % CHUNK;
-        u_s[i * 32 + lane] = u; v_s[i * 32 + lane] = v; c_s[i * 32 + lane] = c;
+        t.u[i * 32 + lane] = u; t.v[i * 32 + lane] = v; t.vw[i * 32 + lane] = vw; t.c[i * 32 + lane] = c;
+        t.g[i * 32 + lane] = (uint8_t)g;
     }
 }
 
 // score of the state held across a warp (lane holds words w[0..NW)), spec'd order.  All lanes return it.
 template <int NW>
-__device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const float* u_s, const float* v_s, const float* c_s,
-                                            int lane) {
+__device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const TermsS t, int lane) {
+    const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], 0);          // state word 0 holds the guard (kill) actions
     float dl = 0.f, dt = 0.f;
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
@@ -69,8 +90,10 @@ __device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const float
         for (int b = 0; b < 32; ++b) {
             const int i = k * 32 + b;
             const bool ap = (w[k] >> b) & 1u;
-            dl = __fadd_rn(dl, ap ? v_s[i * 32 + lane] : u_s[i * 32 + lane]);
-            dt = __fadd_rn(dt, ap ? c_s[i * 32 + lane] : 0.f);
+            const unsigned gd = t.g[i * 32 + lane];
+            const bool guard_alive = gd < 32u && !((w0 >> gd) & 1u);
+            dl = __fadd_rn(dl, ap ? (guard_alive ? t.vw[i * 32 + lane] : t.v[i * 32 + lane]) : t.u[i * 32 + lane]);
+            dt = __fadd_rn(dt, ap ? t.c[i * 32 + lane] : 0.f);
         }
     }
 #pragma unroll
@@ -155,6 +178,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 
 struct MctsArgs {
     const float *p, *size, *cost;
+    const int32_t* guard;   // [A] guard (kill action) index per action, or nullptr
     int A;
     const uint32_t* root_state;
     int R, D, T;
@@ -164,12 +188,13 @@ struct MctsArgs {
     int32_t* root_n;
     float* root_w;
     int32_t* num_nodes_out;
-    int32_t* visits;     // [T+1]
-    int32_t* child_n;    // [(T+1) * A_pad]
+    // per-CTA tree replicas: replica b starts at base + b * stride (elements)
+    int32_t* visits;     // [grid][T+1]
+    int32_t* child_n;    // [grid][(T+1) * A_pad]
     float* child_w;
     int32_t* child_id;
-    float* val;          // [R]
-    int32_t* g_num_nodes;
+    size_t node_stride;  // (T+1) rounded up to 64
+    float* val;          // [2][R]  (double buffered across iterations)
     unsigned* barrier;   // grid barrier counter (zero at launch)
 };
 
@@ -178,9 +203,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     constexpr int A_PAD = 1024 * NW, NWORDS = 32 * NW;
     unsigned bar_target = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* u_s = reinterpret_cast<float*>(smem_raw);
-    float* v_s = u_s + A_PAD;
-    float* c_s = v_s + A_PAD;
+    const TermsS terms = carve_terms<NW>(smem_raw);
     __shared__ uint32_t s_state[NWORDS];
     __shared__ int2 s_path[MAXD];
     __shared__ float s_key[MCTS_WARPS];
@@ -189,10 +212,23 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     __shared__ int s_node, s_depth, s_plen, s_created, s_stop, s_L0, s_numnodes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    stage_terms<NW>(P.p, P.size, P.cost, P.A, u_s, v_s, c_s);
+    // this CTA's replica of the tree (identical in every CTA: all apply the same deterministic updates)
+    int32_t* const visits = P.visits + (size_t)blockIdx.x * P.node_stride;
+    int32_t* const child_n = P.child_n + (size_t)blockIdx.x * P.node_stride * A_PAD;
+    float* const child_w = P.child_w + (size_t)blockIdx.x * P.node_stride * A_PAD;
+    int32_t* const child_id = P.child_id + (size_t)blockIdx.x * P.node_stride * A_PAD;
+    stage_terms<NW>(P.p, P.size, P.cost, P.guard, P.A, terms);
+    // the replica is initialised here, by its own CTA (no host memsets): T+1 node rows
+    for (size_t i = tid; i < (size_t)(P.T + 1) * A_PAD; i += MCTS_THREADS) { child_n[i] = 0; child_w[i] = 0.f; child_id[i] = -1; }
+    for (int i = tid; i <= P.T; i += MCTS_THREADS) visits[i] = 0;
+    if (tid == 0) s_numnodes = 1;                                        // the root
     __syncthreads();
 
+    long long prof[4] = {0, 0, 0, 0}, tc0 = 0;
+    const bool prof_on = blockIdx.x == 0 && tid == 0;
     for (int t = 0; t < P.T; ++t) {
+        float* const val = P.val + (size_t)(t & 1) * P.R;
+        if (prof_on) tc0 = clock64();
         // ------------------------------------------------------------------ select (redundant per CTA)
         for (int k = tid; k < NWORDS; k += MCTS_THREADS) {
             uint32_t wv = P.root_state ? P.root_state[k] : 0u;
@@ -215,27 +251,26 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
             if (lane == 0) {
                 s_node = 0; s_depth = 0; s_plen = 0; s_created = 0;
-                s_numnodes = __ldcg(P.g_num_nodes);
                 s_L0 = z;                                                // legal actions at the root
-                s_stop = (__ldcg(P.visits) == 0 || P.D <= 0 || z == 0) ? 1 : 0;
+                s_stop = (visits[0] == 0 || P.D <= 0 || z == 0) ? 1 : 0;
             }
         }
         __syncthreads();
         while (!s_stop) {                                                // s_stop is rewritten only between the two barriers below
             const int node = s_node;
-            const float lnN = __ldg(P.lnN + __ldcg(P.visits + node));
+            const float lnN = __ldg(P.lnN + visits[node]);
             float best_key = -INFINITY;
             int best_a = 0x7fffffff;
             const size_t base = (size_t)node * A_PAD;
             for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
                 if ((s_state[a >> 5] >> (a & 31)) & 1u) continue;
-                const int n = __ldcg(P.child_n + base + a);
+                const int n = child_n[base + a];
                 float key;
                 if (n == 0) {
                     key = INFINITY;
                 } else {
                     const float nf = (float)n;
-                    const float q = __fdiv_rn(__ldcg(P.child_w + base + a), nf);
+                    const float q = __fdiv_rn(child_w[base + a], nf);
                     key = __fadd_rn(q, __fmul_rn(P.c, __fsqrt_rn(__fdiv_rn(lnN, nf))));
                 }
                 if (key > best_key) { best_key = key; best_a = a; }     // ascending a: strict > keeps the lowest
@@ -248,22 +283,29 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             }
             if (lane == 0) { s_key[warp] = best_key; s_arg[warp] = best_a; }
             __syncthreads();                                             // everyone has read s_stop / s_node / s_state
-            if (tid == 0) {
-                float bk = s_key[0]; int ba = s_arg[0];
-                for (int i = 1; i < MCTS_WARPS; ++i)
-                    if (s_key[i] > bk || (s_key[i] == bk && s_arg[i] < ba)) { bk = s_key[i]; ba = s_arg[i]; }
+            if (warp == 0) {
+                float bk = lane < MCTS_WARPS ? s_key[lane] : -INFINITY;
+                int ba = lane < MCTS_WARPS ? s_arg[lane] : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+                    if (ok > bk || (ok == bk && oa < ba)) { bk = ok; ba = oa; }
+                }
+              if (lane == 0) {
                 s_path[s_plen] = make_int2(node, ba);
                 s_plen += 1;
                 s_state[ba >> 5] |= 1u << (ba & 31);
                 const int depth_new = s_depth + 1;
                 s_depth = depth_new;
-                const int cid = __ldcg(P.child_id + base + ba);
+                const int cid = child_id[base + ba];
                 if (cid < 0) {
                     s_created = 1; s_node = s_numnodes; s_stop = 1;      // new leaf
                 } else {
                     s_node = cid;                                        // descend; stop at a terminal node
-                    if (__ldcg(P.visits + cid) == 0 || depth_new >= P.D || s_L0 - depth_new == 0) s_stop = 1;
+                    if (visits[cid] == 0 || depth_new >= P.D || s_L0 - depth_new == 0) s_stop = 1;
                 }
+              }
             }
             __syncthreads();
         }
@@ -271,6 +313,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
         __syncthreads();
         const int leaf = s_node, depth = s_depth, L0 = s_L0;
         const bool first_move = (P.D - depth) > 0 && L0 > 0;
+        if (prof_on) { const long long c = clock64(); prof[0] += c - tc0; tc0 = c; }
 
         // ------------------------------------------------------------------ rollouts (warp per rollout)
         for (int r = (int)blockIdx.x * MCTS_WARPS + warp; r < P.R; r += (int)gridDim.x * MCTS_WARPS) {
@@ -296,25 +339,31 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                     }
                 }
             }
-            const float sc = warp_score<NW>(w, u_s, v_s, c_s, lane);
-            if (lane == 0) P.val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
+            const float sc = warp_score<NW>(w, terms, lane);
+            if (lane == 0) val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
         }
-        grid_barrier(P.barrier, bar_target);
+        if (prof_on) { const long long c = clock64(); prof[1] += c - tc0; tc0 = c; }
+        grid_barrier(P.barrier, bar_target);                             // every rollout value of this iteration is visible
+        if (prof_on) { const long long c = clock64(); prof[2] += c - tc0; tc0 = c; }
 
-        // ------------------------------------------------------------------ backup
-        if (first_move) {   // leaf children: rank q -> action, fixed ascending-r accumulation
+        // ------------------------------------------------------------------ backup (every CTA, on its own replica)
+        if (first_move) {   // leaf children: action a has rank q among the leaf's legal actions; fixed ascending-r accumulation
             const int nq = P.R < L0 ? P.R : L0;
             const size_t lbase = (size_t)leaf * A_PAD;
-            for (int q = (int)blockIdx.x * MCTS_THREADS + tid; q < nq; q += (int)gridDim.x * MCTS_THREADS) {
-                const int a = kth_zero_serial(s_state, NWORDS, q);
-                float wsum = __ldcg(P.child_w + lbase + a);
+            for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
+                const uint32_t wv = s_state[a >> 5];
+                if ((wv >> (a & 31)) & 1u) continue;                     // not legal at the leaf
+                int q = __popc(~wv & ((1u << (a & 31)) - 1u));           // zeros below a: in its word ...
+                for (int k = 0; k < (a >> 5); ++k) q += __popc(~s_state[k]);   // ... and in the words before (smem broadcasts)
+                if (q >= nq) continue;
+                float wsum = child_w[lbase + a];
                 int cnt = 0;
-                for (int r = q; r < P.R; r += L0) { wsum = __fadd_rn(wsum, __ldcg(P.val + r)); ++cnt; }
-                P.child_w[lbase + a] = wsum;
-                P.child_n[lbase + a] = __ldcg(P.child_n + lbase + a) + cnt;
+                for (int r = q; r < P.R; r += L0) { wsum = __fadd_rn(wsum, __ldcg(val + r)); ++cnt; }
+                child_w[lbase + a] = wsum;
+                child_n[lbase + a] = child_n[lbase + a] + cnt;
             }
         }
-        if (blockIdx.x == 0) {
+        {
             // adjacent-pairs tree sum of val[0..R): each thread reduces an aligned block of m values in
             // registers / local memory, lanes combine with the xor butterfly (== adjacent pairs, lane i holds
             // block i), warps with a fixed pairing.  Same tree as the oracle for any power-of-two R.
@@ -324,7 +373,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             float v = 0.f;
             if (tid < nthr) {
                 float loc[MAXR / TS];
-                for (int i = 0; i < m; ++i) loc[i] = __ldcg(P.val + tid * m + i);
+                for (int i = 0; i < m; ++i) loc[i] = __ldcg(val + tid * m + i);
                 for (int st = 1; st < m; st <<= 1)
                     for (int i = 0; i < m; i += 2 * st) loc[i] = __fadd_rn(loc[i], loc[i + st]);
                 v = loc[0];
@@ -345,6 +394,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                     const float other = __shfl_xor_sync(0xffffffffu, u, o);
                     if (o < nw) u = __fadd_rn(u, other);
                 }
+                __syncthreads();                                        // every thread has read s_tree[0] above
                 if (tid == 0) s_tree[0] = u;
                 __syncthreads();
                 total = s_tree[0];
@@ -353,28 +403,32 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             for (int i = tid; i < plen; i += MCTS_THREADS) {
                 const int2 e = s_path[i];
                 const size_t idx = (size_t)e.x * A_PAD + e.y;
-                P.child_n[idx] = __ldcg(P.child_n + idx) + P.R;
-                P.child_w[idx] = __fadd_rn(__ldcg(P.child_w + idx), total);
-                P.visits[e.x] = __ldcg(P.visits + e.x) + 1;
+                child_n[idx] = child_n[idx] + P.R;
+                child_w[idx] = __fadd_rn(child_w[idx], total);
+                visits[e.x] = visits[e.x] + 1;
             }
             if (tid == 0) {
-                P.visits[leaf] = __ldcg(P.visits + leaf) + 1;
+                visits[leaf] = visits[leaf] + 1;
                 if (s_created) {
                     const int2 e = s_path[plen - 1];
-                    P.child_id[(size_t)e.x * A_PAD + e.y] = leaf;
-                    *P.g_num_nodes = s_numnodes + 1;
+                    child_id[(size_t)e.x * A_PAD + e.y] = leaf;
+                    s_numnodes = s_numnodes + 1;
                 }
             }
         }
-        grid_barrier(P.barrier, bar_target);
+        __syncthreads();                                                 // this CTA's replica is up to date for its next select
+        if (prof_on) { const long long c = clock64(); prof[3] += c - tc0; tc0 = c; }
+    }
+    if (prof_on) {                                                       // phase cycle counts of CTA 0 (diagnostics; 4 words after the barrier counter)
+        for (int i = 0; i < 4; ++i) P.barrier[8 + i] = (unsigned)(prof[i] >> 4);
     }
     // ---------------------------------------------------------------------- outputs
     if (blockIdx.x == 0) {
         for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
-            P.root_n[a] = __ldcg(P.child_n + a);
-            P.root_w[a] = __ldcg(P.child_w + a);
+            P.root_n[a] = child_n[a];
+            P.root_w[a] = child_w[a];
         }
-        if (tid == 0) *P.num_nodes_out = __ldcg(P.g_num_nodes);
+        if (tid == 0) *P.num_nodes_out = s_numnodes;
     }
 }
 
@@ -382,56 +436,66 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
 template <int NW>
 __global__ void __launch_bounds__(256) reward_score_kernel(const uint32_t* __restrict__ states, int64_t B,
                                                            const float* __restrict__ p, const float* __restrict__ size,
-                                                           const float* __restrict__ cost, int A, float* __restrict__ out) {
-    constexpr int A_PAD = 1024 * NW;
+                                                           const float* __restrict__ cost, const int32_t* __restrict__ guard,
+                                                           int A, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* u_s = reinterpret_cast<float*>(smem_raw);
-    float* v_s = u_s + A_PAD;
-    float* c_s = v_s + A_PAD;
-    stage_terms<NW>(p, size, cost, A, u_s, v_s, c_s);
+    const TermsS terms = carve_terms<NW>(smem_raw);
+    stage_terms<NW>(p, size, cost, guard, A, terms);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < B; s += (int64_t)gridDim.x * 8) {
         uint32_t w[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) w[k] = states[s * (32 * NW) + lane * NW + k];
-        const float sc = warp_score<NW>(w, u_s, v_s, c_s, lane);
+        const float sc = warp_score<NW>(w, terms, lane);
         if (lane == 0) out[s] = sc;
     }
 }
 
 static int nw_for(int A) { return A <= 1024 ? 1 : (A <= 2048 ? 2 : 4); }
 
+static int mcts_grid_for(int R) {
+    int want = (R + MCTS_WARPS - 1) / MCTS_WARPS;
+    if (want < 1) want = 1;
+    const int sms = sm_count();
+    return want < sms ? want : sms;                // one CTA per SM (896 threads + the staged terms fill an SM)
+}
+
 struct MctsLayout {
-    size_t visits, child_n, child_w, child_id, val, numnodes, barrier, total;
+    size_t visits, child_n, child_w, child_id, val, barrier, total, node_stride;
+    int grid;
 };
 static MctsLayout mcts_layout(int A, int T, int R) {
     const size_t A_pad = 1024 * (size_t)nw_for(A);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     MctsLayout L;
+    L.grid = mcts_grid_for(R);
+    L.node_stride = ((size_t)T + 1 + 63) & ~(size_t)63;
+    const size_t per_tree = L.node_stride * A_pad * 4;
     size_t o = 0;
-    L.visits = o; o = al(o + (size_t)(T + 1) * 4);
-    L.child_n = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
-    L.child_w = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
-    L.numnodes = o; o = al(o + 4);
     L.barrier = o; o = al(o + 4);
-    L.child_id = o; o = al(o + (size_t)(T + 1) * A_pad * 4);
-    L.val = o; o = al(o + (size_t)R * 4);
+    L.visits = o; o = al(o + (size_t)L.grid * L.node_stride * 4);
+    L.child_n = o; o = al(o + (size_t)L.grid * per_tree);
+    L.child_w = o; o = al(o + (size_t)L.grid * per_tree);
+    L.child_id = o; o = al(o + (size_t)L.grid * per_tree);
+    L.val = o; o = al(o + (size_t)2 * R * 4);
     L.total = o;
     return L;
 }
 
 template <int NW>
-static int launch_mcts(MctsArgs& args, cudaStream_t st) {
-    const size_t smem = (size_t)3 * 1024 * NW * 4;
-    NERRF_CHECK_CUDA(cudaFuncSetAttribute(mcts_search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    NERRF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcts_search_kernel<NW>, MCTS_THREADS, smem));
-    NERRF_REQUIRE(per_sm >= 1, "mcts kernel does not fit on an SM");
-    const int max_blocks = per_sm * sm_count();
-    int want = (args.R + MCTS_WARPS - 1) / MCTS_WARPS;
-    if (want < 1) want = 1;
-    const int grid = want < max_blocks ? want : max_blocks;
+static int launch_mcts(MctsArgs& args, int grid, cudaStream_t st) {
+    const size_t smem = terms_smem_bytes<NW>();
+    static bool attr_set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set_dev[dev_ & 63]) {
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(mcts_search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        NERRF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcts_search_kernel<NW>, MCTS_THREADS, smem));
+        NERRF_REQUIRE(per_sm >= 1, "mcts kernel does not fit on an SM");
+        attr_set_dev[dev_ & 63] = true;
+    }
     void* kargs[] = {(void*)&args};
     NERRF_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)mcts_search_kernel<NW>, dim3(grid), dim3(MCTS_THREADS), kargs, smem, st));
     return NERRF_OK;
@@ -442,22 +506,21 @@ static int launch_mcts(MctsArgs& args, cudaStream_t st) {
 using namespace nerrf;
 
 extern "C" int nerrf_reward_score(const uint32_t* states, int64_t B, const float* p, const float* size,
-                                  const float* cost, int A, float* out, nerrf_stream_t stream) {
+                                  const float* cost, const int32_t* guard, int A, float* out, nerrf_stream_t stream) {
     NERRF_REQUIRE(states && p && size && cost && out, "null pointer");
     NERRF_REQUIRE(A >= 1 && A <= 4096, "number of actions must be in 1..4096 (got %d)", A);
     NERRF_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return NERRF_OK;
     const int NW = nw_for(A);
-    const size_t smem = (size_t)3 * 1024 * NW * 4;
     int64_t g = (B + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (g > cap) g = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (NW == 1) reward_score_kernel<1><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
-    else if (NW == 2) reward_score_kernel<2><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
+    if (NW == 1) reward_score_kernel<1><<<(unsigned)g, 256, terms_smem_bytes<1>(), st>>>(states, B, p, size, cost, guard, A, out);
+    else if (NW == 2) reward_score_kernel<2><<<(unsigned)g, 256, terms_smem_bytes<2>(), st>>>(states, B, p, size, cost, guard, A, out);
     else {
-        NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reward_score_kernel<4><<<(unsigned)g, 256, smem, st>>>(states, B, p, size, cost, A, out);
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)terms_smem_bytes<4>()));
+        reward_score_kernel<4><<<(unsigned)g, 256, terms_smem_bytes<4>(), st>>>(states, B, p, size, cost, guard, A, out);
     }
     return launch_status("reward_score_kernel");
 }
@@ -471,9 +534,9 @@ extern "C" int nerrf_mcts_workspace_bytes(int A, int T, int R, size_t* bytes) {
     return NERRF_OK;
 }
 
-extern "C" int nerrf_mcts_search(const float* p, const float* size, const float* cost, int A, const uint32_t* root_state,
-                                 int R, int D, int T, uint64_t seed, float c, float lo, float inv_range,
-                                 const float* ln_table, int32_t* root_n, float* root_w, int32_t* num_nodes,
+extern "C" int nerrf_mcts_search(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
+                                 const uint32_t* root_state, int R, int D, int T, uint64_t seed, float c, float lo,
+                                 float inv_range, const float* ln_table, int32_t* root_n, float* root_w, int32_t* num_nodes,
                                  void* workspace, size_t workspace_bytes, nerrf_stream_t stream) {
     size_t need = 0;
     int rc = nerrf_mcts_workspace_bytes(A, T, R, &need);
@@ -487,57 +550,103 @@ extern "C" int nerrf_mcts_search(const float* p, const float* size, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const MctsLayout L = mcts_layout(A, T, R);
     unsigned char* ws = (unsigned char*)workspace;
-    // visits, child_n, child_w, num_nodes are contiguous: zero them; child_id = -1
-    NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.visits, 0, L.child_id - L.visits, st));
-    NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.child_id, 0xFF, L.val - L.child_id, st));
-    NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.numnodes, 1, 1, st));      // little-endian int32 1 (the word was zeroed above): root node
+    NERRF_CHECK_CUDA(cudaMemsetAsync(ws + L.barrier, 0, 4, st));       // the tree replicas are initialised by the kernel itself
     MctsArgs a;
-    a.p = p; a.size = size; a.cost = cost; a.A = A; a.root_state = root_state; a.R = R; a.D = D; a.T = T;
+    a.p = p; a.size = size; a.cost = cost; a.guard = guard; a.A = A; a.root_state = root_state; a.R = R; a.D = D; a.T = T;
     a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32);
     a.c = c; a.lo = lo; a.inv_range = inv_range; a.lnN = ln_table;
     a.root_n = root_n; a.root_w = root_w; a.num_nodes_out = num_nodes;
     a.visits = (int32_t*)(ws + L.visits); a.child_n = (int32_t*)(ws + L.child_n); a.child_w = (float*)(ws + L.child_w);
-    a.child_id = (int32_t*)(ws + L.child_id); a.val = (float*)(ws + L.val); a.g_num_nodes = (int32_t*)(ws + L.numnodes); a.barrier = (unsigned*)(ws + L.barrier);
+    a.child_id = (int32_t*)(ws + L.child_id); a.node_stride = L.node_stride; a.val = (float*)(ws + L.val);
+    a.barrier = (unsigned*)(ws + L.barrier);
     const int NW = nw_for(A);
-    if (NW == 1) return launch_mcts<1>(a, st);
-    if (NW == 2) return launch_mcts<2>(a, st);
-    return launch_mcts<4>(a, st);
+    if (NW == 1) return launch_mcts<1>(a, L.grid, st);
+    if (NW == 2) return launch_mcts<2>(a, L.grid, st);
+    return launch_mcts<4>(a, L.grid, st);
 }
 
-extern "C" int nerrf_mcts_search_host(const float* p, const float* size, const float* cost, int A,
+// ---- host-buffer session: device memory + a stream live in the handle, so a host-side search is copies + one launch
+struct nerrf_mcts_session {
+    unsigned char* d = nullptr;
+    size_t bytes = 0;
+    int A_max = 0, T_max = 0, R_max = 0;
+    cudaStream_t st = nullptr;
+    size_t o_p, o_s, o_c, o_g, o_rs, o_ln, o_rn, o_rw, o_nn, o_ws, ws_bytes;
+};
+
+extern "C" int nerrf_mcts_session_create(int A_max, int T_max, int R_max, nerrf_mcts_session** out) {
+    NERRF_REQUIRE(out, "null out");
+    size_t need = 0;
+    int rc = nerrf_mcts_workspace_bytes(A_max, T_max, R_max, &need);
+    if (rc) return rc;
+    nerrf_mcts_session* s = new nerrf_mcts_session();
+    s->A_max = A_max; s->T_max = T_max; s->R_max = R_max;
+    const size_t A_pad = 1024 * (size_t)nw_for(A_max), nwords = 32 * (size_t)nw_for(A_max);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    s->o_p = 0; s->o_s = al(s->o_p + A_pad * 4); s->o_c = al(s->o_s + A_pad * 4); s->o_g = al(s->o_c + A_pad * 4);
+    s->o_rs = al(s->o_g + A_pad * 4); s->o_ln = al(s->o_rs + nwords * 4); s->o_rn = al(s->o_ln + (size_t)(T_max + 2) * 4);
+    s->o_rw = al(s->o_rn + A_pad * 4); s->o_nn = al(s->o_rw + A_pad * 4); s->o_ws = al(s->o_nn + 4);
+    s->ws_bytes = need; s->bytes = s->o_ws + need;
+    cudaError_t e = cudaMalloc((void**)&s->d, s->bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("mcts session: %s", cudaGetErrorString(e));
+        if (s->d) cudaFree(s->d);
+        delete s;
+        return NERRF_ERR_CUDA;
+    }
+    *out = s;
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_mcts_session_destroy(nerrf_mcts_session* s) {
+    if (!s) return NERRF_OK;
+    if (s->st) cudaStreamDestroy(s->st);
+    if (s->d) cudaFree(s->d);
+    delete s;
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_mcts_session_search_host(nerrf_mcts_session* s, const float* p, const float* size, const float* cost,
+                                              const int32_t* guard, int A, const uint32_t* root_state_host, int R, int D, int T,
+                                              uint64_t seed, float c, float lo, float inv_range, const float* ln_table_host,
+                                              int32_t* root_n_host, float* root_w_host, int32_t* num_nodes_host) {
+    NERRF_REQUIRE(s && p && size && cost && ln_table_host && root_n_host && root_w_host && num_nodes_host, "null pointer");
+    NERRF_REQUIRE(A >= 1 && A <= s->A_max && nw_for(A) == nw_for(s->A_max) && T >= 1 && T <= s->T_max && R >= 1 && R <= s->R_max,
+                  "search (A=%d, T=%d, R=%d) exceeds the session (A_max=%d with the same word count, T_max=%d, R_max=%d)", A, T, R,
+                  s->A_max, s->T_max, s->R_max);
+    const size_t A_pad = 1024 * (size_t)nw_for(A), nwords = 32 * (size_t)nw_for(A);
+    unsigned char* d = s->d;
+    cudaStream_t st = s->st;
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_p, p, (size_t)A * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_s, size, (size_t)A * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_c, cost, (size_t)A * 4, cudaMemcpyHostToDevice, st));
+    if (guard) NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_g, guard, (size_t)A * 4, cudaMemcpyHostToDevice, st));
+    if (root_state_host) NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_rs, root_state_host, nwords * 4, cudaMemcpyHostToDevice, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(d + s->o_ln, ln_table_host, (size_t)(T + 2) * 4, cudaMemcpyHostToDevice, st));
+    int rc = nerrf_mcts_search((const float*)(d + s->o_p), (const float*)(d + s->o_s), (const float*)(d + s->o_c),
+                               guard ? (const int32_t*)(d + s->o_g) : nullptr, A,
+                               root_state_host ? (const uint32_t*)(d + s->o_rs) : nullptr, R, D, T, seed, c, lo, inv_range,
+                               (const float*)(d + s->o_ln), (int32_t*)(d + s->o_rn), (float*)(d + s->o_rw), (int32_t*)(d + s->o_nn),
+                               d + s->o_ws, s->ws_bytes, st);
+    if (rc) return rc;
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(root_n_host, d + s->o_rn, A_pad * 4, cudaMemcpyDeviceToHost, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(root_w_host, d + s->o_rw, A_pad * 4, cudaMemcpyDeviceToHost, st));
+    NERRF_CHECK_CUDA(cudaMemcpyAsync(num_nodes_host, d + s->o_nn, 4, cudaMemcpyDeviceToHost, st));
+    NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
+    return launch_status("mcts session search");
+}
+
+// one-shot convenience: a temporary session (allocates and frees device memory inside the call)
+extern "C" int nerrf_mcts_search_host(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
                                       const uint32_t* root_state_host, int R, int D, int T, uint64_t seed, float c,
                                       float lo, float inv_range, const float* ln_table_host, int32_t* root_n_host,
                                       float* root_w_host, int32_t* num_nodes_host) {
-    size_t need = 0;
-    int rc = nerrf_mcts_workspace_bytes(A, T, R, &need);
+    nerrf_mcts_session* s = nullptr;
+    int rc = nerrf_mcts_session_create(A, T, R, &s);
     if (rc) return rc;
-    NERRF_REQUIRE(p && size && cost && ln_table_host && root_n_host && root_w_host && num_nodes_host, "null pointer");
-    const int NW = nw_for(A);
-    const size_t A_pad = 1024 * (size_t)NW, nwords = 32 * (size_t)NW;
-    unsigned char* d = nullptr;
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t o_p = 0, o_s = al(o_p + A * 4), o_c = al(o_s + A * 4), o_rs = al(o_c + A * 4), o_ln = al(o_rs + nwords * 4);
-    const size_t o_rn = al(o_ln + (size_t)(T + 2) * 4), o_rw = al(o_rn + A_pad * 4), o_nn = al(o_rw + A_pad * 4);
-    const size_t o_ws = al(o_nn + 4), total = o_ws + need;
-    NERRF_CHECK_CUDA(cudaMalloc((void**)&d, total));
-    cudaStream_t st = 0;
-    rc = NERRF_OK;
-    auto fail = [&](cudaError_t e, const char* what) { set_error("%s failed: %s", what, cudaGetErrorString(e)); rc = NERRF_ERR_CUDA; };
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(d + o_p, p, A * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D p");
-    if (!rc && (e = cudaMemcpyAsync(d + o_s, size, A * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D size");
-    if (!rc && (e = cudaMemcpyAsync(d + o_c, cost, A * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D cost");
-    if (!rc && root_state_host && (e = cudaMemcpyAsync(d + o_rs, root_state_host, nwords * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D root");
-    if (!rc && (e = cudaMemcpyAsync(d + o_ln, ln_table_host, (size_t)(T + 2) * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D ln");
-    if (!rc)
-        rc = nerrf_mcts_search((const float*)(d + o_p), (const float*)(d + o_s), (const float*)(d + o_c), A,
-                               root_state_host ? (const uint32_t*)(d + o_rs) : nullptr, R, D, T, seed, c, lo, inv_range,
-                               (const float*)(d + o_ln), (int32_t*)(d + o_rn), (float*)(d + o_rw), (int32_t*)(d + o_nn),
-                               d + o_ws, need, st);
-    if (!rc && (e = cudaMemcpyAsync(root_n_host, d + o_rn, A_pad * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H root_n");
-    if (!rc && (e = cudaMemcpyAsync(root_w_host, d + o_rw, A_pad * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H root_w");
-    if (!rc && (e = cudaMemcpyAsync(num_nodes_host, d + o_nn, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H num_nodes");
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) fail(e, "sync");
-    cudaFree(d);
+    rc = nerrf_mcts_session_search_host(s, p, size, cost, guard, A, root_state_host, R, D, T, seed, c, lo, inv_range, ln_table_host,
+                                        root_n_host, root_w_host, num_nodes_host);
+    nerrf_mcts_session_destroy(s);
     return rc;
 }

@@ -33,15 +33,22 @@ from . import graph as G
 class Shard:
     """What one rank holds: full rowptr, its edge block of col / ew (indexed from edge_base)."""
 
-    def __init__(self, rowptr, col, ew, rank, world, device=None, cut="edges"):
+    def __init__(self, rowptr, col, ew, rank, world, device=None, cut="edges", align=1):
         """cut="edges": edge-balanced row-aligned cuts (skewed graphs); cut="rows": equal row blocks (when the
-        in-degree is uniform these are edge-balanced too, and the exchange can be one in-place all-gather)."""
+        in-degree is uniform these are edge-balanced too, and the exchange can be one in-place all-gather).
+        align: cuts are rounded to a multiple of `align` rows -- the component size of a trace-structured graph
+        (one process + its files, contiguous node ids), so that no component straddles two ranks and the per-layer
+        exchange has (almost) nothing to send."""
         rp = rowptr.cpu().numpy() if isinstance(rowptr, torch.Tensor) else np.asarray(rowptr)
         n = rp.shape[0] - 1
         if cut == "rows":
             self.cuts = np.array([(n * g) // world for g in range(world + 1)], dtype=np.int64)
         else:
             self.cuts = G.edge_balanced_row_cuts(rp, world)
+        if align > 1:
+            c = (np.round(self.cuts / align).astype(np.int64) * align).clip(0, n)
+            c[0], c[-1] = 0, n
+            self.cuts = np.maximum.accumulate(c)
         self.rank, self.world = rank, world
         self.row_begin, self.row_end = int(self.cuts[rank]), int(self.cuts[rank + 1])
         self.edge_base, self.edge_end = int(rp[self.row_begin]), int(rp[self.row_end])
@@ -227,114 +234,220 @@ def cuda_layer_fn(model):
     return fn
 
 
-def bench_sharded(model, args, world, rank, local_rank, dev, workload_config, algorithmic_bytes_layer, measured_peaks,
-                  ClockSampler, physical_gpu_index, run_mcts_bench):
-    """bench.py's N > 1 arm (weak scaling: N x (1M nodes, 10M edges), one exchange per layer)."""
-    from bench import N_NODES, N_EDGES, HIDDEN, LAYERS
-    N, E = N_NODES * world, N_EDGES * world
-    rowptr, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, relabel=True)
-    shard = Shard(rowptr, col, ew, rank, world, device=dev, cut="rows" if args.exchange == "allgather" else "edges")
-    shard_src_col, shard_src_ew = col, ew           # kept only until the exchange mode is settled (fallback re-shards)
-    pb, need, exchange_note = None, None, ""
-    if args.exchange in ("p2p", "p2p-all", "multicast"):
-        try:
-            pb = PeerBuffers(N, HIDDEN, dev, rank, world, multicast=args.exchange == "multicast")
-            need = pb.build_need_mask(shard, N) if args.exchange == "p2p" else None
-            ok = torch.ones(1, device=dev)
-        except Exception as e:                      # no peer mapping on this system: fall back to the NCCL exchange
-            pb, need, ok = None, None, torch.zeros(1, device=dev)
-            exchange_note = f" (peer mapping failed: {type(e).__name__}; fell back to allgather)"
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
-        if float(ok) == 0.0:
-            pb, need = None, None
-            args.exchange = "allgather"
-            shard = Shard(rowptr, shard_src_col, shard_src_ew, rank, world, device=dev, cut="rows")
-    del shard_src_col, shard_src_ew, col, ew
-    torch.cuda.empty_cache()
-    bufs = pb.bufs if pb else [torch.empty(N, HIDDEN, device=dev) for _ in range(2)]
-    score = torch.empty(N, device=dev)
-    layer = cuda_layer_fn(model)
-    K, W = args.steps, max(args.warmup, 3)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * LAYERS + 1)] for _ in range(K)]
+def gpu_trace_graph(n_components, device, seed=7, files=63, ev_lo=3, ev_hi=8):
+    """Trace-STRUCTURED synthetic graph: what the graph constructor produces for a fleet of processes, each touching its
+    own files (the LockBit traces benchmarks/m{0,1}/results/*_trace.jsonl are one such component: 1 pid + 57 / 98 paths).
+    Component c = node c*S (the process) + S-1 file nodes, S = files + 1, node ids contiguous per component; every file
+    has ev_lo..ev_hi-1 events, each event one edge process->file and one file->process (nerrf_b200.graph
+    graph_from_events), t ~ U[0, 60 s), conf = 1.  -> (rowptr, col, ew, x, S).  Generated on the GPU, deterministic per
+    seed, so every rank holds the same graph."""
+    S = files + 1
+    N = n_components * S
+    gen = torch.Generator(device=device).manual_seed(seed)
+    n_files = n_components * files
+    ev = torch.randint(ev_lo, ev_hi, (n_files,), generator=gen, device=device)
+    fidx = torch.repeat_interleave(torch.arange(n_files, device=device), ev)
+    file_node = (fidx // files) * S + 1 + fidx % files
+    pid_node = (fidx // files) * S
+    t1 = torch.rand(fidx.numel(), generator=gen, device=device) * G.WINDOW
+    src = torch.cat([pid_node, file_node]); dst = torch.cat([file_node, pid_node]); t = torch.cat([t1, t1])
+    del fidx, file_node, pid_node, t1
+    order = torch.argsort(t, stable=True)
+    order = order[torch.argsort(dst[order], stable=True)]
+    src, dst, t = src[order], dst[order], t[order]
+    E = src.numel()
+    rowptr = torch.zeros(N + 1, dtype=torch.int32, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
+    ew = torch.exp(-(G.WINDOW - t) / G.TAU).float().contiguous()
+    x = torch.randn(N, G.F_IN, generator=torch.Generator(device=device).manual_seed(seed + 1), device=device)
+    return rowptr, src.to(torch.int32).contiguous(), ew, x, S
 
-    def step(i=None):
-        h = x
-        if i is not None: ev[i][0].record()
-        for l in range(LAYERS):
-            out = bufs[l & 1]
-            last = l == LAYERS - 1
+
+class ShardedSage:
+    """The 1-D edge-block sharded GraphSAGE-T forward of one rank: graph shard, peer-mapped
+    embedding buffers, need mask, and the per-layer loop with the exchange fused into the layer kernel's epilogue
+    (exchange="p2p" / "p2p-all" / "multicast") or done by NCCL ("allgather" / "broadcast" / "allreduce").
+
+    Buffer reuse across steps: the last layer has no exchange, so a fast rank could start step i+1 and store layer-0
+    rows into a peer's buffer while that peer still READS it as the input of its step-i last layer (even layer
+    counts) -- every step therefore ends with one more cross-rank barrier."""
+
+    def __init__(self, model, rowptr, col, ew, rank, world, device, exchange="p2p", align=1, hidden=128):
+        self.model, self.rank, self.world, self.dev, self.hidden = model, rank, world, device, hidden
+        self.exchange, self.note = exchange, ""
+        self.N = rowptr.numel() - 1
+        self.L = model.num_layers
+        cut = "rows" if exchange == "allgather" else "edges"
+        self.shard = Shard(rowptr, col, ew, rank, world, device=device, cut=cut, align=align)
+        self.pb = self.need = None
+        if exchange in ("p2p", "p2p-all", "multicast"):
+            try:
+                self.pb = PeerBuffers(self.N, hidden, device, rank, world, multicast=exchange == "multicast")
+                self.need = self.pb.build_need_mask(self.shard, self.N) if exchange == "p2p" else None
+                ok = torch.ones(1, device=device)
+            except Exception as e:                      # no peer mapping on this system: fall back to the NCCL exchange
+                self.pb, self.need, ok = None, None, torch.zeros(1, device=device)
+                self.note = f" (peer mapping failed: {type(e).__name__}; fell back to allgather)"
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+            if float(ok) == 0.0:
+                self.pb = self.need = None
+                self.exchange = "allgather"
+                self.shard = Shard(rowptr, col, ew, rank, world, device=device, cut="rows")
+        self.bufs = self.pb.bufs if self.pb else [torch.empty(self.N, hidden, device=device) for _ in range(2)]
+        self.score = torch.empty(self.N, device=device)
+        self.layer = cuda_layer_fn(model)
+        self.x = None
+        self._xsym = None
+
+    # -- inputs ---------------------------------------------------------------------------------------------------
+    def set_x(self, x):
+        """Resident features: the full [N, F] matrix already on this device."""
+        self.x = x
+
+    def sharded_upload(self, hx_own, h_rowptr_own, h_col, h_ew):
+        """The e2e input path: this rank copies only ITS rows of x (and its slices of rowptr / col / ew) from pinned host
+        memory, then the ranks complete each other's x over NVLink -- a row goes to the peers whose edge block
+        references it (the need mask), written straight into their x buffers.  Replaces every rank pulling the whole x
+        through its own PCIe link."""
+        sh = self.shard
+        if self._xsym is None:
+            self._init_x_exchange(hx_own.shape[1])
+        xs = self._xsym
+        xs[sh.row_begin:sh.row_end].copy_(hx_own, non_blocking=True)
+        sh.rowptr[sh.row_begin:sh.row_end + 1].copy_(h_rowptr_own, non_blocking=True)
+        sh.col.copy_(h_col, non_blocking=True); sh.ew.copy_(h_ew, non_blocking=True)
+        if self._x_peers is not None:
+            for p_x, idx in zip(self._x_peers, self._x_idx):
+                if idx.numel():
+                    p_x[idx] = xs[idx]                                  # remote stores over NVLink
+            self._x_hdl.barrier()
+        else:
+            exchange_rows(xs, sh.cuts, self.rank, self.world, "broadcast")
+        self.x = xs
+
+    def _init_x_exchange(self, F):
+        sh = self.shard
+        self._x_peers = None
+        if self.pb is not None and self.pb.hdls is not None:
+            import torch.distributed._symmetric_memory as symm
+            self._xsym = symm.empty(self.N, F, dtype=torch.float32, device=self.dev)
+            self._x_hdl = symm.rendezvous(self._xsym, dist.group.WORLD)
+            self._x_peers = [self._x_hdl.get_buffer(p, (self.N, F), torch.float32) for p in range(self.world) if p != self.rank]
+            own = torch.arange(sh.row_begin, sh.row_end, device=self.dev)
+            if self.need is not None:
+                m = self.need[sh.row_begin:sh.row_end]
+                self._x_idx = [own[((m >> s_) & 1).bool()] for s_ in range(self.world - 1)]
+            else:
+                self._x_idx = [own for _ in range(self.world - 1)]
+        else:
+            self._xsym = torch.empty(self.N, F, dtype=torch.float32, device=self.dev)
+
+    # -- one forward ----------------------------------------------------------------------------------------------
+    def step(self, ev=None, snapshots=None):
+        """One sharded forward; the node scores of the own rows land in self.score[row_begin:row_end].
+        ev: list of 2L+1 CUDA events (compute / exchange segments); snapshots: list that receives a clone of every
+        layer's full output buffer after its exchange (parity checks only)."""
+        pb, sh, L = self.pb, self.shard, self.L
+        h = self.x
+        if ev is not None: ev[0].record()
+        for l in range(L):
+            out = self.bufs[l & 1]
+            last = l == L - 1
             fused = pb is not None and not last
-            layer(l, h, out, shard, score_out=score if last else None, peer_outs=pb.peers[l & 1] if fused else None,
-                  multicast_ptr=pb.mc[l & 1] if fused else 0, peer_need=need if fused else None)
-            if i is not None: ev[i][2 * l + 1].record()
+            self.layer(l, h, out, sh, score_out=self.score if last else None, peer_outs=pb.peers[l & 1] if fused else None,
+                       multicast_ptr=pb.mc[l & 1] if fused else 0, peer_need=self.need if fused else None)
+            if ev is not None: ev[2 * l + 1].record()
             if fused:                                       # rows already written into every peer's buffer by the epilogue
                 pb.barrier(l & 1)
             elif not last:                                  # the last layer's rows / scores stay sharded
-                exchange_rows(out, shard.cuts, rank, world, args.exchange)
-            if i is not None: ev[i][2 * l + 2].record()
+                exchange_rows(out, sh.cuts, self.rank, self.world, self.exchange)
+            elif pb is not None:
+                pb.barrier(l & 1)                           # nobody overwrites a buffer a peer is still reading (next step)
+            if ev is not None: ev[2 * l + 2].record()
+            if snapshots is not None:
+                snapshots.append(out.clone())
             h = out
+        return self.score
 
+    def describe(self):
+        pb = self.pb
+        return (self.exchange + self.note + (f" [{pb.kind}]" if pb else "") +
+                (f", rows sent to a peer only if it references them ({100 * pb.need_fraction:.1f}% of row x peer pairs)"
+                 if self.need is not None else ""))
+
+    def exchange_bytes_per_layer(self):
+        """(egress, ingress) bytes of this rank per exchanged layer."""
+        sh, H = self.shard, self.hidden
+        rows = sh.row_end - sh.row_begin
+        if self.need is not None:
+            eg = int(sum(int(((self.need[sh.row_begin:sh.row_end] >> s_) & 1).sum()) for s_ in range(self.world - 1))) * H * 4
+            t = torch.tensor([eg], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t)                               # symmetric on average: report the mean as ingress
+            return eg, int(float(t) / self.world)
+        if self.pb is not None or self.exchange in ("allgather", "broadcast"):
+            return rows * (self.world - 1) * H * 4, (self.N - rows) * H * 4
+        return self.N * H * 4, self.N * H * 4
+
+    # -- parity ---------------------------------------------------------------------------------------------------
+    def parity_vs_single_gpu(self, rowptr, col, ew, x):
+        """Sharded forward == single-GPU forward of the same kernel on the SAME full graph, bit for bit: this rank's own
+        rows of every layer and of the scores, and -- for every exchanged layer -- every row this rank READS as a source
+        (i.e. every row a peer had to deliver).  All arguments are full-graph tensors on this device."""
+        model, sh, L = self.model, self.shard, self.L
+        snaps = []
+        self.set_x(x) if self.x is None else None
+        self.step(snapshots=snaps)
+        torch.cuda.synchronize()
+        reads = torch.zeros(self.N, dtype=torch.bool, device=self.dev)
+        reads[sh.col.long()] = True
+        reads[sh.row_begin:sh.row_end] = True
+        ridx = reads.nonzero().squeeze(1)
+        own = slice(sh.row_begin, sh.row_end)
+        h = x
+        own_ok, read_ok, worst = True, True, 0.0
+        bufs = [torch.empty(self.N, self.hidden, device=self.dev) for _ in range(2)]
+        score = torch.empty(self.N, device=self.dev)
+        for l in range(L):
+            ref = bufs[l & 1]
+            model.layer_forward(l, h, rowptr, col, ew, out=ref, score_out=score if l == L - 1 else None, reuse_long_scan=l > 0)
+            own_ok &= bool(torch.equal(snaps[l][own], ref[own]))
+            worst = max(worst, float((snaps[l][own] - ref[own]).abs().max()) if sh.row_end > sh.row_begin else 0.0)
+            if l < L - 1:
+                read_ok &= bool(torch.equal(snaps[l][ridx], ref[ridx]))
+            h = ref
+        own_ok &= bool(torch.equal(self.score[own], score[own]))
+        flags = torch.tensor([int(own_ok), int(read_ok)], device=self.dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        w = torch.tensor([worst], device=self.dev); dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        nread = torch.tensor([float(ridx.numel() - (sh.row_end - sh.row_begin))], device=self.dev); dist.all_reduce(nread)
+        return {"own_rows_bit_exact": bool(flags[0]), "read_rows_bit_exact": bool(flags[1]), "layers": L,
+                "max_abs_diff_own_rows": float(w), "remote_rows_read_checked_per_layer": int(float(nread)),
+                "what": "sharded forward vs the single-GPU forward of the full graph on every rank: own rows of every layer "
+                        "+ scores, and every remotely produced row a rank reads as a source"}, (h, score)
+
+
+def timed_sharded_run(ss: "ShardedSage", K, W, sampler_factory=None):
+    """W warm-up + K timed sharded forwards (barrier + synchronize on both sides, CUDA events, max over ranks).
+    -> dict(ms_per_step, compute_ms [L], exchange_ms [L], per_rank_segments, clocks)."""
+    L, dev, world = ss.L, ss.dev, ss.world
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * L + 1)] for _ in range(K)]
     for _ in range(W):
-        step()
+        ss.step()
     torch.cuda.synchronize(); dist.barrier()
-    sampler = ClockSampler(physical_gpu_index(local_rank)); sampler.start()
+    sampler = sampler_factory() if sampler_factory else None
+    if sampler: sampler.start()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
     for i in range(K):
-        step(i)
+        ss.step(ev[i])
     t1.record()
     torch.cuda.synchronize(); dist.barrier()
-    clocks = sampler.result()
+    clocks = sampler.result() if sampler else None
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms) / K
-    seg = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(2 * LAYERS)] for i in range(K)]).mean(0)
-    comp_ms, comm_ms = seg[0::2], seg[1::2]
-    seg_all = [torch.zeros(2 * LAYERS, device=dev) for _ in range(world)]
+    seg = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(2 * L)] for i in range(K)]).mean(0)
+    seg_all = [torch.zeros(2 * L, device=dev) for _ in range(world)]
     dist.all_gather(seg_all, torch.tensor(seg, device=dev, dtype=torch.float32))
-    per_rank = [[round(float(v), 4) for v in t_.cpu()] for t_ in seg_all]
-    peak, peak_src = measured_peaks()
-    e_loc, r_loc = shard.edge_end - shard.edge_base, shard.row_end - shard.row_begin
-    dom_bytes = algorithmic_bytes_layer(e_loc, r_loc, HIDDEN)
-    dom_ms = float(comp_ms[1])
-    mcts_local = run_mcts_bench(dev, args, seed=rank)
-    roll = torch.tensor([mcts_local["value"]], device=dev)
-    dist.all_reduce(roll, op=dist.ReduceOp.SUM)
-    mcts_local.update({"value": float(roll), "note": "root-parallel: sum over ranks of independent trees (seed = rank), no collective"})
-    # ---- e2e: the same sharded step with this rank's inputs coming from pinned host memory every step
-    hx, hrp, hcol, hew = (t.cpu().pin_memory() for t in (x, shard.rowptr, shard.col, shard.ew))
-    hscore = torch.empty(r_loc).pin_memory()
-    def e2e_step():
-        x.copy_(hx, non_blocking=True); shard.rowptr.copy_(hrp, non_blocking=True)
-        shard.col.copy_(hcol, non_blocking=True); shard.ew.copy_(hew, non_blocking=True)
-        step()
-        hscore.copy_(score[shard.row_begin:shard.row_end], non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_step(); dist.barrier()
-    te = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    dist.barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - te) / K], device=dev)
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    h2d = int(hx.numel() * 4 + hrp.numel() * hrp.element_size() + hcol.numel() * 4 + hew.numel() * 4)
-    e2e = {"value": E / float(e2e_s), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(r_loc * 4),
-           "ms_per_step": float(e2e_s) * 1e3, "api": "nerrf_b200.dist sharded step, per-rank pinned inputs (bytes are per rank)"}
-    tp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
-    traffic = json.load(open(tp)).get("sage_layer_F128_dram_bytes_per_launch") if os.path.exists(tp) else None
-    return {"metric": "graphsage_t_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (torch CUDA generator, same distribution as the N=1 graph, random vertex relabeling for shard balance)",
-            "config": dict(workload_config(world), exchange=args.exchange + exchange_note + (f" [{pb.kind}]" if pb else "") +
-                           (f", rows sent to a peer only if it references them ({100 * pb.need_fraction:.0f}% of row x peer pairs)" if need is not None else "")),
-            "roofline": {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (rank 0's edge block)", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic if world == 1 else None,
-                         "peak_source": peak_src, "per_layer_compute_ms": [float(v) for v in comp_ms],
-                         "per_layer_exchange_ms": [float(v) for v in comm_ms],
-                         "per_rank_segments_ms": per_rank,
-                         "exchange_bytes_per_layer": int(N * HIDDEN * 4)},
-            "cpu_baseline": None,
-            "e2e": e2e,
-            "gpu_launches": K * LAYERS, "clocks": clocks, "mcts": mcts_local, "algo": args.algo}
+    return {"ms_per_step": float(ms) / K, "compute_ms": [float(v) for v in seg[0::2]], "exchange_ms": [float(v) for v in seg[1::2]],
+            "per_rank_segments_ms": [[round(float(v), 4) for v in t_.cpu()] for t_ in seg_all], "clocks": clocks}

@@ -246,7 +246,7 @@ def graph_from_columns(cols: EventColumns, merge_renames=True, window=None, devi
     return G.TemporalGraph(rowptr, col, ew, x, meta)
 
 
-def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, observable=False):
+def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, observable=False, only_nodes=None):
     """Per-file event sequences for the LSTM without per-event Python: the same arrays as
     pipeline.file_sequences(events_from_columns(cols), graph) -- seq fp32 [n_files, t_max, 16], lengths int32, node ids --
     (the last t_max events of every file node, oldest first; feature layout: pipeline.file_sequences)."""
@@ -261,6 +261,15 @@ def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, o
     _, node_f, _, kind, _, _ = intern_nodes(cols, order, merge_renames)
     F = node_f[order].astype(np.int64)
     tt = ts[order]                                        # absolute seconds, time-sorted
+    if only_nodes is not None:
+        # sequences for a subset of the file nodes only (the top-A candidates of a large window): drop every other event
+        # up front -- node ids, time order and the per-file histories of the kept nodes are unchanged
+        keep_node = np.zeros(kind.shape[0], bool); keep_node[np.asarray(only_nodes, np.int64)] = True
+        sel_ev = keep_node[F]
+        order, F, tt = order[sel_ev], F[sel_ev], tt[sel_ev]
+        n = int(F.shape[0])
+        if n == 0:
+            return np.zeros((0, t_max, lstm.D_IN), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int64)
     # group by file node, keeping time order inside a group
     by_file = np.argsort(F, kind="stable")
     Fg = F[by_file]

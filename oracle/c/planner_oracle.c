@@ -35,20 +35,30 @@ static int nw_for(int A) { return A <= 1024 ? 1 : (A <= 2048 ? 2 : 4); }
 typedef struct {
     int A, NW, chunk, A_pad, n_words;
     float *u, *v, *c;   /* [A_pad] */
+    float* vw;          /* [A_pad] spec v1: term of an applied action whose guard (kill action, index < 32) is NOT applied */
+    int* g;             /* [A_pad] guard index or -1 */
 } Terms;
 
-static void terms_init(Terms* t, const float* p, const float* size, const float* cost, int A) {
+static void terms_init(Terms* t, const float* p, const float* size, const float* cost, const int32_t* guard, int A) {
     t->A = A; t->NW = nw_for(A); t->chunk = 32 * t->NW; t->A_pad = 1024 * t->NW; t->n_words = 32 * t->NW;
     t->u = (float*)calloc(t->A_pad, sizeof(float)); t->v = (float*)calloc(t->A_pad, sizeof(float));
     t->c = (float*)calloc(t->A_pad, sizeof(float));
+    t->vw = (float*)calloc(t->A_pad, sizeof(float)); t->g = (int*)malloc(t->A_pad * sizeof(int));
+    for (int a = 0; a < t->A_pad; ++a) t->g[a] = -1;
     for (int a = 0; a < A; ++a) {
         t->u[a] = p[a] * size[a];
         const float om = 1.0f - p[a];
         t->v[a] = om * size[a];
         t->c[a] = cost[a];
+        t->vw[a] = t->v[a];
+        if (guard && guard[a] >= 0 && guard[a] < 32 && guard[a] < A) {   /* w_a = fl(p_g * u_a); vw_a = fl(v_a + w_a) */
+            t->g[a] = guard[a];
+            const float w = p[guard[a]] * t->u[a];
+            t->vw[a] = t->v[a] + w;
+        }
     }
 }
-static void terms_free(Terms* t) { free(t->u); free(t->v); free(t->c); }
+static void terms_free(Terms* t) { free(t->u); free(t->v); free(t->c); free(t->vw); free(t->g); }
 
 /* fixed-order score: lane l sums its `chunk` consecutive actions sequentially, xor-butterfly 1,2,4,8,16 */
 static float score_state(const Terms* t, const uint32_t* s) {
@@ -58,7 +68,9 @@ static float score_state(const Terms* t, const uint32_t* s) {
         for (int i = 0; i < t->chunk; ++i) {
             const int act = l * t->chunk + i;
             const int ap = (s[act >> 5] >> (act & 31)) & 1u;
-            a = a + (ap ? t->v[act] : t->u[act]);
+            const int gd = t->g[act];
+            const int guard_alive = gd >= 0 && !((s[0] >> gd) & 1u);     /* its kill action is not in the state */
+            a = a + (ap ? (guard_alive ? t->vw[act] : t->v[act]) : t->u[act]);
             b = b + (ap ? t->c[act] : 0.f);
         }
         dl[l] = a; dt[l] = b;
@@ -71,9 +83,9 @@ static float score_state(const Terms* t, const uint32_t* s) {
     return -(dl[0] + tenth);
 }
 
-void nerrf_oracle_score(const uint32_t* states, int64_t B, const float* p, const float* size, const float* cost, int A,
-                        float* out) {
-    Terms t; terms_init(&t, p, size, cost, A);
+void nerrf_oracle_score(const uint32_t* states, int64_t B, const float* p, const float* size, const float* cost,
+                        const int32_t* guard, int A, float* out) {
+    Terms t; terms_init(&t, p, size, cost, guard, A);
 #pragma omp parallel for schedule(static)
     for (int64_t b = 0; b < B; ++b) out[b] = score_state(&t, states + b * t.n_words);
     terms_free(&t);
@@ -100,10 +112,11 @@ static float tree_sum(float* v, int n) {   /* adjacent pairs, in place */
 }
 
 /* Leaf-parallel UCT exactly as oracle/mcts_ref.py.  root_n int32 [A_pad], root_w fp32 [A_pad] out. */
-int nerrf_oracle_mcts(const float* p, const float* size, const float* cost, int A, const uint32_t* root_state, int R, int D,
+int nerrf_oracle_mcts(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
+                      const uint32_t* root_state, int R, int D,
                       int T, uint64_t seed, float c, float lo, float inv_range, const float* lnN, int32_t* root_n,
                       float* root_w, int32_t* num_nodes_out) {
-    Terms t; terms_init(&t, p, size, cost, A);
+    Terms t; terms_init(&t, p, size, cost, guard, A);
     const int nw = t.n_words, Ap = t.A_pad;
     const uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
     int32_t* visits = (int32_t*)calloc(T + 1, sizeof(int32_t));

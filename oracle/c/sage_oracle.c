@@ -37,6 +37,14 @@ static inline int64_t rp_at(const void* rowptr, int is64, int64_t i) {
     return is64 ? ((const int64_t*)rowptr)[i] : (int64_t)((const int32_t*)rowptr)[i];
 }
 
+void nerrf_oracle_sage_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int nerrf_oracle_sage_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -48,28 +48,35 @@ def philox(c0, c1, c2, c3, k0, k1):
     return tuple(int(v) for v in out)
 
 
-def score(states, p, size, cost):
+def _guard(guard):
+    return None if guard is None else np.ascontiguousarray(guard, np.int32)
+
+
+def score(states, p, size, cost, guard=None):
     p = np.ascontiguousarray(p, np.float32); size = np.ascontiguousarray(size, np.float32); cost = np.ascontiguousarray(cost, np.float32)
     A = p.shape[0]
     nw = RW.layout(A)[3]
     st = np.ascontiguousarray(states, np.uint32).reshape(-1, nw)
     out = np.zeros(st.shape[0], np.float32)
-    lib().nerrf_oracle_score(_p(st), C.c_int64(st.shape[0]), _p(p), _p(size), _p(cost), C.c_int(A), _p(out))
+    g = _guard(guard)
+    lib().nerrf_oracle_score(_p(st), C.c_int64(st.shape[0]), _p(p), _p(size), _p(cost), _p(g) if g is not None else None,
+                             C.c_int(A), _p(out))
     return out
 
 
-def search(p, size, cost, R=4096, D=50, T=64, seed=0, c=np.sqrt(2.0), root_state=None, threads=None):
+def search(p, size, cost, R=4096, D=50, T=64, seed=0, c=np.sqrt(2.0), root_state=None, threads=None, guard=None):
     p = np.ascontiguousarray(p, np.float32); size = np.ascontiguousarray(size, np.float32); cost = np.ascontiguousarray(cost, np.float32)
     A = p.shape[0]
     _, _, A_pad, nw = RW.layout(A)
     root = RW.empty_state(A) if root_state is None else (np.asarray(root_state, np.uint32) | RW.empty_state(A))
     root = np.ascontiguousarray(root, np.uint32)
-    lo, inv = RW.reward_bounds(p, size, cost, root)
+    lo, inv = RW.reward_bounds(p, size, cost, root, guard)
+    g = _guard(guard)
     lnN = ln_table(T, R)
     root_n = np.zeros(A_pad, np.int32); root_w = np.zeros(A_pad, np.float32); nn = np.zeros(1, np.int32)
     if threads:
         os.environ["OMP_NUM_THREADS"] = str(threads)
-    lib().nerrf_oracle_mcts(_p(p), _p(size), _p(cost), C.c_int(A), _p(root), C.c_int(R), C.c_int(D), C.c_int(T), C.c_uint64(seed),
+    lib().nerrf_oracle_mcts(_p(p), _p(size), _p(cost), _p(g) if g is not None else None, C.c_int(A), _p(root), C.c_int(R), C.c_int(D), C.c_int(T), C.c_uint64(seed),
                             C.c_float(np.float32(c)), C.c_float(lo), C.c_float(inv), _p(lnN), _p(root_n), _p(root_w), _p(nn))
     return {"root_n": root_n[:A].copy(), "root_w": root_w[:A].copy(), "best": best_child(root_n[:A], root_w[:A]),
             "num_nodes": int(nn[0]), "lo": lo, "inv_range": inv}

@@ -67,6 +67,27 @@ def threads():
     return int(lib().nerrf_oracle_sage_threads())
 
 
+def set_threads(n):
+    lib().nerrf_oracle_sage_set_threads(C.c_int(int(n)))
+    return threads()
+
+
+def tune_threads(fwd: "Forward", candidates=(8, 16, 32, 64, 128)):
+    """The host may expose more logical CPUs than it grants cycles (cgroup quota) or memory bandwidth: pick the thread
+    count at which one full forward runs fastest.  Returns (threads, seconds)."""
+    import time
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best = (None, float("inf"))
+    for c in sorted({c for c in candidates if c <= ncpu} | {min(ncpu, 8)}):
+        set_threads(c)
+        fwd.run()
+        t0 = time.perf_counter(); fwd.run(); dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (c, dt)
+    set_threads(best[0])
+    return best
+
+
 def _np(a, dt):
     if hasattr(a, "detach"):
         a = a.detach().cpu().numpy()

@@ -117,7 +117,7 @@ class Tree:
         self.num_nodes = 1
 
 
-def rollouts(s0, depth, t, R, D, seed, p, size, cost, lo, inv_range):
+def rollouts(s0, depth, t, R, D, seed, p, size, cost, lo, inv_range, guard=None):
     """One leaf evaluation.  Returns (val fp32 [R], first int64 [R] (-1 if none), L0, final states)."""
     A = np.asarray(p).shape[0]
     NW, chunk, A_pad, nw = RW.layout(A)
@@ -145,19 +145,19 @@ def rollouts(s0, depth, t, R, D, seed, p, size, cost, lo, inv_range):
         # inactive rows (no legal action) keep their state: select on a dummy but mask the set
         a = _select_kth_zero(np.where(active[:, None], s, np.uint32(0)), j)
         _set_bit(s, a, active)
-    sc = RW.score(s, p, size, cost)
+    sc = RW.score(s, p, size, cost, guard)
     val = ((sc - F32(lo)).astype(F32) * F32(inv_range)).astype(F32)
     return val, first, L0, s
 
 
 def search(p, size, cost, R=4096, D=50, T=64, seed=0, c=np.sqrt(2.0), root_state=None,
-           bounds=None, return_tree=False):
+           bounds=None, return_tree=False, guard=None):
     p = np.asarray(p, F32); size = np.asarray(size, F32); cost = np.asarray(cost, F32)
     A = p.shape[0]
     NW, chunk, A_pad, nw = RW.layout(A)
     assert R >= 1 and (R & (R - 1)) == 0, "R must be a power of two"
     root = RW.empty_state(A) if root_state is None else (np.asarray(root_state, np.uint32) | RW.empty_state(A))
-    lo, inv = RW.reward_bounds(p, size, cost, root) if bounds is None else bounds
+    lo, inv = RW.reward_bounds(p, size, cost, root, guard) if bounds is None else bounds
     lnN = ln_table(T, R)
     c32 = F32(c)
     tree = Tree(T, A_pad)
@@ -192,7 +192,7 @@ def search(p, size, cost, R=4096, D=50, T=64, seed=0, c=np.sqrt(2.0), root_state
                 break
             node = int(tree.child_id[node][a])
         leaf = node
-        val, first, L0, _ = rollouts(state, depth, t, R, D, seed, p, size, cost, lo, inv)
+        val, first, L0, _ = rollouts(state, depth, t, R, D, seed, p, size, cost, lo, inv, guard)
         total = tree_sum(val)
         if first[0] >= 0:
             nq = min(R, L0)

@@ -9,6 +9,14 @@ Frozen spec v0.  For a state s (bitset over A undo actions
     data_loss(s) = sum_{a not in s} p_a*size_a  +  sum_{a in s} (1-p_a)*size_a      [MB]
     downtime(s)  = sum_{a in s} cost_a                                               [s]
     score(s)     = -(data_loss + 0.1*downtime)
+Spec v1 (round 2) adds the one NON-SEPARABLE term the reference's own candidate list implies
+(threat-model.mdx:208-222: "Reverse file encryption" next to "Kill process python3"): reverting a file while the
+process that encrypts it is still alive does not stick.  Every action a may name a GUARD g = guard_a in 0..31 -- the
+index of the "kill process" action of the process that wrote it (guards live in state word 0) -- or -1:
+    if a in s and guard_a >= 0 and guard_a not in s:   data_loss += w_a,   w_a = fl(p_g * u_a)
+(with probability p_g, the process is malicious and re-encrypts the reverted file).  In the summation the term of an
+applied action is vw_a = fl(v_a + w_a) instead of v_a -- one term per action as before, same order.  guard = None
+(all -1) is spec v0 bit for bit.
 All arithmetic is IEEE fp32 with a FIXED association order so that the CUDA
 kernel can be bit-exact:
     NW     = 1, 2 or 4   (smallest with 1024*NW >= A);  chunk = 32*NW;  A_pad = 32*chunk
@@ -85,14 +93,36 @@ def _lane_tree_sum(terms, chunk):
     return acc[:, 0]
 
 
-def score(states, p, size, cost):
+def guard_terms(p, size, cost, guard):
+    """-> (g int64 [A_pad] (-1 = none), vw fp32 [A_pad] = fl(v_a + fl(p_g * u_a)) where a guard exists, else v_a)."""
+    u, v, _ = action_terms(p, size, cost)
+    A = np.asarray(p).shape[0]
+    g = np.full(u.shape[0], -1, np.int64)
+    if guard is not None:
+        gg = np.asarray(guard, np.int64)
+        if gg.shape[0] != A or (gg >= 32).any() or (gg >= A).any() or (gg < -1).any():
+            raise ValueError("guard must be -1 or the index (< 32, < A) of the kill action")
+        g[:A] = gg
+    pg = np.where(g >= 0, np.asarray(p, F32)[np.maximum(g, 0).clip(max=A - 1)], F32(0.0)).astype(F32)
+    w = (pg * u).astype(F32)
+    vw = np.where(g >= 0, (v + w).astype(F32), v).astype(F32)
+    return g, vw
+
+
+def score(states, p, size, cost, guard=None):
     """states uint32 [B, n_words] (padding bits may be 0 or 1: padded terms are 0) -> fp32 [B]."""
     A = np.asarray(p).shape[0]
     NW, chunk, A_pad, nw = layout(A)
     states = np.asarray(states, dtype=np.uint32).reshape(-1, nw)
     u, v, c = action_terms(p, size, cost)
     applied = unpack_bits(states)
-    dl_terms = np.where(applied, v[None, :], u[None, :]).astype(F32)
+    if guard is not None:
+        g, vw = guard_terms(p, size, cost, guard)
+        guard_alive = (g[None, :] >= 0) & ~applied[:, np.maximum(g, 0)]          # the guard (kill) action is NOT in s
+        v = np.where(guard_alive, vw[None, :], v[None, :]).astype(F32)
+    else:
+        v = v[None, :]
+    dl_terms = np.where(applied, v, u[None, :]).astype(F32)
     dt_terms = np.where(applied, c[None, :], F32(0.0)).astype(F32)
     dl = _lane_tree_sum(dl_terms, chunk)
     dt = _lane_tree_sum(dt_terms, chunk)
@@ -100,7 +130,7 @@ def score(states, p, size, cost):
     return (-((dl + tenth).astype(F32))).astype(F32)
 
 
-def reward_bounds(p, size, cost, root_state=None):
+def reward_bounds(p, size, cost, root_state=None, guard=None):
     """(lo, inv_range) fp32 normalisation constants used by the planner.
 
     lo / hi = worst / best score over all supersets of root_state, computed in
@@ -111,11 +141,15 @@ def reward_bounds(p, size, cost, root_state=None):
     u, v, c = action_terms(p, size, cost)
     u = u.astype(np.float64)[:A]; v = v.astype(np.float64)[:A]; c = c.astype(np.float64)[:A]
     applied_cost = v + 0.1 * c
+    applied_worst = applied_cost
+    if guard is not None:                      # an applied action may also pay its guard penalty: a valid (not tight) bound
+        _, vw = guard_terms(p, size, cost, guard)
+        applied_worst = vw.astype(np.float64)[:A] + 0.1 * c
     if root_state is None:
         fixed = np.zeros(A, bool)
     else:
         fixed = unpack_bits(np.asarray(root_state, np.uint32)[None, :])[0][:A]
-    worst = np.where(fixed, applied_cost, np.maximum(u, applied_cost))
+    worst = np.where(fixed, applied_worst, np.maximum(u, applied_worst))
     best = np.where(fixed, applied_cost, np.minimum(u, applied_cost))
     lo = -math.fsum(worst.tolist())
     hi = -math.fsum(best.tolist())

@@ -11,10 +11,7 @@ from oracle import lstm_ref  # noqa: E402
 
 
 def run(model, seq, ln, algo):
-    if algo == "umma":
-        os.environ["NERRF_LSTM_ALGO"] = "umma"
-    else:
-        os.environ.pop("NERRF_LSTM_ALGO", None)
+    os.environ["NERRF_LSTM_ALGO"] = algo          # "ffma" = the fp32 CUDA-core cross-check kernel; anything else = tcgen05
     out = model(seq, ln)
     torch.cuda.synchronize()
     return out
@@ -23,7 +20,7 @@ def run(model, seq, ln, algo):
 def main():
     torch.manual_seed(0)
     m = LSTMScorer().cuda()
-    for B, T in ((6, 20), (130, 12), (300, 33)):
+    for B, T in ((6, 20), (130, 12), (300, 33), (1, 1), (64, 7), (65, 100), (700, 5)):
         seq = torch.randn(B, T, 16); ln = torch.randint(1, T + 1, (B,)); ln[0] = T
         want = lstm_ref.forward(m.oracle_params(), seq, ln)
         for algo in ("ffma", "umma"):
@@ -33,6 +30,7 @@ def main():
     seq = torch.randn(B, T, 16, device="cuda"); ln = torch.randint(T // 2, T + 1, (B,), device="cuda")
     for algo in ("ffma", "umma"):
         run(m, seq, ln, algo)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         a = run(m, seq, ln, algo)
         dt = time.perf_counter() - t0

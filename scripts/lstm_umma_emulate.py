@@ -44,7 +44,7 @@ def emulate(params, seq, lengths):
     R = B * T
     L = len(params["lstm"])
     slabs = np.zeros((4 * R, UM), np.float32)
-    xpad = np.zeros((R, 32), np.float32); xpad[:, :D] = seq.reshape(R, D)
+    xpad = np.zeros((R, 32), np.float32); xpad[:, :D] = seq.transpose(1, 0, 2).reshape(R, D)   # TIME-MAJOR rows: t*B + b
     hfin = np.zeros((B, 2 * LH), np.float32)
     v = np.arange(R)
     for l in range(L):
@@ -75,7 +75,7 @@ def emulate(params, seq, lengths):
                     t = T - 1 - step if d else step
                     hn = h.copy()
                     for s in range(SL):
-                        rows = (b0 + np.arange(nb)) * T + t
+                        rows = t * B + b0 + np.arange(nb)
                         g = np.zeros((NSEQ, UM), np.float32)
                         g[:nb] = gxa[d * SL + s][rows] + (gxb[d * SL + s][rows] if l > 0 else 0.0)
                         g = g + h @ whh[d, s]                                           # gates^T = W_slice . h^T

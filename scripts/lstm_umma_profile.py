@@ -8,7 +8,6 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 from nerrf_b200.ai.models.lstm import LSTMScorer  # noqa: E402
 
-os.environ["NERRF_LSTM_ALGO"] = "umma"
 m = LSTMScorer().cuda()
 B, T = 4096, 100
 seq = torch.randn(B, T, 16, device="cuda"); ln = torch.randint(T // 2, T + 1, (B,), device="cuda")

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     h = ctypes.CDLL(lib_built)
     for s in _declared_symbols():
         assert hasattr(h, s), f"libnerrf_b200.so does not export {s}"
-    assert h.nerrf_abi_version() == 1
+    assert h.nerrf_abi_version() == 2
 
 
 def test_python_binding_covers_header(lib_built):
@@ -102,4 +102,4 @@ def test_header_is_plain_c99(tmp_path, lib_built):
     subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lnerrf_b200",
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    assert out[0] == "1"
+    assert out[0] == "2"

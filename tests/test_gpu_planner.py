@@ -105,3 +105,67 @@ def test_plan_reverts_exactly_the_attacked_files():
     pl = mcts.plan(act, max_steps=40, n_rollouts=1024, depth=40, iterations=8)
     assert sorted(pl.actions) == sorted(np.nonzero(attacked)[0].tolist())
     assert all(b > a for a, b in zip(pl.scores, pl.scores[1:]))
+
+
+# ---------------------------------------------------------------- planner spec v1: guards (non-separable reward)
+def _guarded_actions(A, n_kill, seed):
+    rng = np.random.default_rng(seed)
+    act = _actions(A, seed)
+    size = act.size.copy(); cost = act.cost.copy(); p = act.p.copy()
+    size[:n_kill] = 0.0; cost[:n_kill] = 10.0; cost[n_kill:] = 1.0
+    guard = rng.integers(-1, n_kill, A).astype(np.int32); guard[:n_kill] = -1; guard[-1] = 0
+    return Actions(p, size, cost, guard=guard)
+
+
+@pytest.mark.parametrize("A,n_kill", [(2, 1), (100, 3), (1024, 32), (1500, 7), (4096, 32)])
+def test_guarded_reward_score_bit_exact(A, n_kill):
+    act = _guarded_actions(A, n_kill, A)
+    rng = np.random.default_rng(A)
+    applied = rng.random((129, A)) < rng.random((129, 1))
+    st = rewards.pack_states(applied)
+    got = rewards.score(st, act).cpu().numpy()
+    want = RW.score(st, act.p, act.size, act.cost, act.guard)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    lo, inv = rewards.reward_bounds(act, None)
+    lo2, inv2 = RW.reward_bounds(act.p, act.size, act.cost, None, act.guard)
+    assert lo == lo2 and inv == inv2
+
+
+@pytest.mark.parametrize("A,n_kill,R,D,T,seed", [(12, 2, 64, 8, 30, 1), (100, 5, 256, 20, 20, 2), (1024, 32, 4096, 50, 5, 3),
+                                                  (1500, 7, 512, 30, 4, 4)])
+@pytest.mark.parametrize("host_call", [False, True])
+def test_guarded_mcts_bit_exact(A, n_kill, R, D, T, seed, host_call):
+    act = _guarded_actions(A, n_kill, seed)
+    got = mcts.search(act, None, n_rollouts=R, depth=D, seed=seed, iterations=T, host_call=host_call)
+    want = M.search(act.p, act.size, act.cost, R=R, D=D, T=T, seed=seed, guard=act.guard)
+    assert np.array_equal(got.root_n, want["root_n"]) and np.array_equal(got.root_w.view(np.uint32), want["root_w"].view(np.uint32))
+    assert got.best == want["best"] and got.num_nodes == want["num_nodes"]
+
+
+def test_search_finds_what_the_threshold_rule_cannot():
+    """VERDICT r1 weak #10.  1 kill action + 8 guarded reversions: every single action lowers the reward, so a
+    per-action threshold (and a one-step greedy validation) applies nothing; the optimum applies all nine.  The tree
+    search must recommend the kill first (its subtree is the only one whose rollouts see the reversions pay off), and
+    plan() with a two-move validation horizon must reach the optimum."""
+    p = np.array([0.9] * 9, np.float32); size = np.array([0.0] + [1.0] * 8, np.float32)
+    cost = np.array([10.0] + [1.0] * 8, np.float32); guard = np.array([-1] + [0] * 8, np.int32)
+    act = Actions(p, size, cost, guard=guard)
+    st = rewards.pack_states(np.array([[False] * 9, [True] * 9] + [[a == b for b in range(9)] for a in range(9)]))
+    sc = rewards.score(st, act).cpu().numpy()
+    assert (sc[2:] < sc[0]).all() and sc[1] > sc[0] + 3.0
+    r = mcts.search(act, None, n_rollouts=1024, depth=9, seed=0, iterations=32)
+    assert r.best == 0, (r.best, r.root_q)
+    pl = mcts.plan(act, n_rollouts=1024, depth=9, iterations=32, lookahead=True)
+    assert sorted(pl.actions) == list(range(9)) and pl.scores[-1] == pytest.approx(float(sc[1]))
+
+
+def test_host_session_reuses_buffers():
+    act = _actions(1024, seed=2)
+    sess = mcts.HostSession(1024, 16, 4096)
+    a = mcts.search(act, None, 4096, 50, 0, iterations=16, host_call=sess)
+    b = mcts.search(act, None, 4096, 50, 0, iterations=16, host_call=True)
+    c = mcts.search(act, None, 4096, 50, 1, iterations=8, host_call=sess)          # smaller search through the same session
+    d = mcts.search(act, None, 4096, 50, 1, iterations=8)
+    assert np.array_equal(a.root_n, b.root_n) and np.array_equal(a.root_w, b.root_w)
+    assert np.array_equal(c.root_n, d.root_n) and np.array_equal(c.root_w, d.root_w)
+    sess.close()
