@@ -127,6 +127,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -177,7 +194,7 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 // activations: |abs error| ~ 2e-7 (ex2.approx + rcp), far inside the 1e-4 spec bound; tanh(x) = 2 sigmoid(2x) - 1
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, sigmoid_fast(2.0f * x), -1.0f); }
 
 // W^T slice [K, 128] (fp32, k-major) -> TMEM planes: thread = gate row f (lane of TMEM), 2 bf16 per 32-bit column.
@@ -361,11 +378,14 @@ __global__ void __launch_bounds__(192, 1) lstm_proj_kernel(ProjArgs P) {
 }
 
 // ================================================================================================ recurrence
-constexpr int REC_EPI_WARPS = 8;                     // warps 0-3: tile slot 0, warps 4-7: tile slot 1
-constexpr int REC_MMA_WARP = 8;
-constexpr int REC_INIT_WARP0 = 9;                    // warps 9-12: slot 0, warps 13-16: slot 1 (accumulator init + exchange)
-constexpr int REC_THREADS = (REC_INIT_WARP0 + 8) * 32;               // 544
-constexpr int GATE_BYTES = 4 * 32 * 32 * 4;          // 16 KB: [gate][seq in chunk of 32][unit] per slot
+// The epilogue is instruction-issue bound (2 warps per scheduler ran at IPC ~0.25 each: 20 k cycles per step,
+// profiles/r02_lstm.md), so every tile slot gets EIGHT epilogue warps: two per TMEM lane quarter, each owning 32 of the
+// tile's 64 sequences.
+constexpr int REC_EPI_WARPS = 16;                    // warps 0-7: tile slot 0, warps 8-15: tile slot 1
+constexpr int REC_MMA_WARP = 16;
+constexpr int REC_INIT_WARP0 = 17;                   // warps 17-20: slot 0, warps 21-24: slot 1 (accumulator init + exchange)
+constexpr int REC_THREADS = (REC_INIT_WARP0 + 8) * 32;               // 800
+constexpr int GATE_BYTES = 2 * 4 * 16 * 32 * 4;      // 16 KB per slot: [half][gate][seq in chunk of 16][unit]
 constexpr size_t REC_SMEM = (size_t)2 * TILE_BYTES_H + 2 * GATE_BYTES + 2 * NSEQ * 4 + 1024 /*align*/ + 128 /*barriers*/;
 static_assert(REC_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(ACC_COL0 + 2 * NSEQ <= TMEM_COLS, "TMEM budget");
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
                 mbar_init(opfull_bar(s), 1);                 // one arrive (+ the bulk copies' transaction bytes)
                 mbar_init(accinit_bar(s), 128);              // the slot's accumulator-init warps
                 mbar_init(accf_bar(s), 1);
-                mbar_init(drained_bar(s), 128);              // the slot's epilogue warps
+                mbar_init(drained_bar(s), 256);              // the slot's epilogue warps
             }
             fence_barrier_init();
         }
@@ -436,12 +456,14 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
 
     if (warp < REC_EPI_WARPS) {
         // =========================================================== epilogue warps of tile slot `slot`
-        const int slot = warp >> 2;
+        const int slot = warp >> 3;
+        const int half = (warp >> 2) & 1;           // sequences [32 half, 32 half + 32) of the tile
         const int wq = warp & 3;                    // TMEM lane quarter = gate type (i, f, g, o)
-        const int et = wq * 32 + lane;              // thread index inside the slot's warpgroup (0..127)
-        float* gs = gate_s + slot * (GATE_BYTES / 4);
+        const int et = wq * 32 + lane;              // thread index inside the (slot, half) warpgroup (0..127)
+        const int bar_id = 1 + slot * 2 + half;     // named barrier of this warpgroup
+        float* gs = gate_s + slot * (GATE_BYTES / 4) + half * (GATE_BYTES / 8);
         int* ls = len_s + slot * NSEQ;
-        const uint32_t acc_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ACC_COL0 + slot * NSEQ);
+        const uint32_t acc_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ACC_COL0 + slot * NSEQ + half * 32);
         const int ucol = slice * 32 + lane;         // hidden unit of this thread in the cell-update phase
         unsigned* counter = P.counter + (size_t)group * 2 + slot;
         uint32_t q = 0;                             // global step index of this (group, slot)
@@ -451,42 +473,41 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
         for (int64_t it = 0; it < items; ++it) {
             const int64_t bt = gd + (2 * it + slot) * groups_dir;
             const int64_t b0 = bt * NSEQ;
-            if (et < NSEQ) { const int64_t b = b0 + et; ls[et] = b < P.B ? P.len[b] : 0; }
-            named_bar(1 + slot, 128);
-            float c_reg[16], h_reg[16];
+            if (et < 32) { const int64_t b = b0 + half * 32 + et; ls[half * 32 + et] = b < P.B ? P.len[b] : 0; }
+            named_bar(bar_id, 128);
+            float c_reg[8], h_reg[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { c_reg[j] = 0.f; h_reg[j] = 0.f; }
+            for (int j = 0; j < 8; ++j) { c_reg[j] = 0.f; h_reg[j] = 0.f; }
             for (int step = 0; step < P.T; ++step, ++q) {
                 const int t = dir ? (P.T - 1 - step) : step;
                 unsigned char* tile = P.out_img + ((size_t)t * P.n_bt + bt) * (2 * TILE_BYTES_H) + (size_t)dir * TILE_BYTES_H;
                 mbar_wait(accf_bar(slot), q & 1u);
                 tc_fence_after();
                 if (prof_on) { const long long c_ = clock64(); pf[0] += c_ - tc; tc = c_; }      // waiting for the MMAs
+                uint32_t v0[16], v1[16];
+                tmem_ld16(acc_addr, v0);
+                tmem_ld16(acc_addr + 16, v1);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(drained_bar(slot));                     // this thread has read all of its accumulator columns
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    // phase A: activated gates of this thread's gate row for 32 sequences -> shared [gate][seq][unit]
-                    uint32_t v[32];
-                    tmem_ld32(acc_addr + (uint32_t)(c * 32), v);
-                    tmem_wait_ld();
-                    if (c == 1) {                                   // this thread has read all of its accumulator columns
-                        tc_fence_before();
-                        mbar_arrive(drained_bar(slot));
-                    }
+                    // phase A: activated gates of this thread's gate row for 16 sequences -> shared [gate][seq][unit]
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        gs[(wq * 32 + j) * 32 + lane] = (wq == 2) ? tanh_fast(x) : sigmoid_fast(x);
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = __uint_as_float(c == 0 ? v0[j] : v1[j]);
+                        gs[(wq * 16 + j) * 32 + lane] = (wq == 2) ? tanh_fast(x) : sigmoid_fast(x);
                     }
-                    named_bar(1 + slot, 128);
-                    // phase B: cell update, thread = (unit lane, sequences wq*8 .. wq*8+7 of the chunk)
+                    named_bar(bar_id, 128);
+                    // phase B: cell update, thread = (unit lane, sequences wq*4 .. wq*4+3 of the chunk)
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int j = wq * 8 + jj;                 // sequence inside the chunk
-                        const int n = c * 32 + j;                  // sequence inside the tile
-                        const float ig = gs[(0 * 32 + j) * 32 + lane], fg = gs[(1 * 32 + j) * 32 + lane];
-                        const float gg = gs[(2 * 32 + j) * 32 + lane], og = gs[(3 * 32 + j) * 32 + lane];
-                        float& cr = c_reg[c * 8 + jj];
-                        float& hr = h_reg[c * 8 + jj];
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = wq * 4 + jj;                 // sequence inside the chunk
+                        const int n = half * 32 + c * 16 + j;      // sequence inside the tile
+                        const float ig = gs[(0 * 16 + j) * 32 + lane], fg = gs[(1 * 16 + j) * 32 + lane];
+                        const float gg = gs[(2 * 16 + j) * 32 + lane], og = gs[(3 * 16 + j) * 32 + lane];
+                        float& cr = c_reg[c * 4 + jj];
+                        float& hr = h_reg[c * 4 + jj];
                         if (t < ls[n]) {
                             cr = fmaf(fg, cr, ig * gg);
                             hr = og * tanh_fast(cr);
@@ -509,12 +530,12 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
                             if (!(lane & 1)) *reinterpret_cast<uint32_t*>(dstp + p * PLANE_BYTES_H) = term[p] | (nb << 16);
                         }
                     }
-                    named_bar(1 + slot, 128);                       // the gate buffer is reused by the next chunk
+                    named_bar(bar_id, 128);                         // the gate buffer is reused by the next chunk
                 }
                 if (prof_on) { const long long c_ = clock64(); pf[1] += c_ - tc; tc = c_; }      // activations + cell update + stores
                 fence_proxy_async_all();                            // generic stores above are read by bulk (async-proxy) copies
-                named_bar(1 + slot, 128);                           // the whole warpgroup has written its h
-                if (et == 0) {
+                named_bar(5 + slot, 256);                           // both halves of the slot have written their h
+                if (half == 0 && et == 0) {
                     __threadfence();
                     atomicAdd(counter, 1u);                          // release: this CTA's h_t slice is published
                 }
@@ -524,9 +545,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int64_t b = b0 + c * 32 + wq * 8 + jj;
-                    if (b < P.B) P.hfin[b * (2 * LH) + dir * LH + ucol] = h_reg[c * 8 + jj];
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int64_t b = b0 + half * 32 + c * 16 + wq * 4 + jj;
+                    if (b < P.B) P.hfin[b * (2 * LH) + dir * LH + ucol] = h_reg[c * 4 + jj];
                 }
         }
         if (prof_on) for (int i = 0; i < 3; ++i) P.counter[128 + i] = (unsigned)(pf[i] >> 6);
@@ -577,16 +598,16 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
                 const float* ra = gxa + (size_t)((int64_t)t * P.Bp + b0) * UM + gcol;
                 const float* rb = gxb ? gxb + (size_t)((int64_t)t * P.Bp + b0) * UM + gcol : nullptr;
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    float ga[32];
+                for (int c = 0; c < 4; ++c) {
+                    float ga[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) ga[j] = __ldg(ra + (size_t)(c * 32 + j) * UM);
+                    for (int j = 0; j < 16; ++j) ga[j] = __ldg(ra + (size_t)(c * 16 + j) * UM);
                     if (rb) {
-                        float gb[32];
+                        float gb[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) gb[j] = __ldg(rb + (size_t)(c * 32 + j) * UM);
+                        for (int j = 0; j < 16; ++j) gb[j] = __ldg(rb + (size_t)(c * 16 + j) * UM);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) ga[j] += gb[j];
+                        for (int j = 0; j < 16; ++j) ga[j] += gb[j];
                     }
                     if (c == 0 && q > 0) {                           // the epilogue of step q-1 has drained the accumulator
                         if (prof_on) { const long long c_ = clock64(); pf[0] += c_ - tc; tc = c_; }   // G_x loads issued + landed
@@ -594,10 +615,10 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
                         tc_fence_after();
                         if (prof_on) { const long long c_ = clock64(); pf[1] += c_ - tc; tc = c_; }   // waiting for the drain
                     }
-                    uint32_t v[32];
+                    uint32_t v[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(ga[j]);
-                    tmem_st32(acc_addr + (uint32_t)(c * 32), v);
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(ga[j]);
+                    tmem_st16(acc_addr + (uint32_t)(c * 16), v);
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -607,11 +628,11 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(RecArgs P) {
                 if (step == 0) {
                     // (the MMAs of the previous tile's last step have retired: its epilogue ran, and this warpgroup waited
                     // for that epilogue's drained barrier above)
-                    named_bar(3 + slot, 128);
+                    named_bar(7 + slot, 128);
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                     for (int i = pt; i < TILE_BYTES_H / 16; i += 128) reinterpret_cast<uint4*>(op_gen)[i] = z;
                     fence_proxy_async();
-                    named_bar(3 + slot, 128);
+                    named_bar(7 + slot, 128);
                     if (pt == 0) mbar_arrive(opfull_bar(slot));
                 } else if (pt == 0) {
                     // every CTA of the group has published step q-1 of this slot (so this CTA's MMA of step q-1, which

@@ -347,6 +347,13 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
         if (prof_on) { const long long c = clock64(); prof[2] += c - tc0; tc0 = c; }
 
         // ------------------------------------------------------------------ backup (every CTA, on its own replica)
+        // the tree-sum operands are requested first, so their L2 latency overlaps the leaf-children pass
+        constexpr int TS = 512;                                         // threads used by the tree sum (power of two)
+        const int m = P.R >= TS ? P.R / TS : 1;
+        const int nthr = P.R / m;                                       // power of two <= TS
+        float loc[MAXR / TS];
+        if (tid < nthr)
+            for (int i = 0; i < m; ++i) loc[i] = __ldcg(val + tid * m + i);
         if (first_move) {   // leaf children: action a has rank q among the leaf's legal actions; fixed ascending-r accumulation
             const int nq = P.R < L0 ? P.R : L0;
             const size_t lbase = (size_t)leaf * A_PAD;
@@ -358,7 +365,13 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
                 if (q >= nq) continue;
                 float wsum = child_w[lbase + a];
                 int cnt = 0;
-                for (int r = q; r < P.R; r += L0) { wsum = __fadd_rn(wsum, __ldcg(val + r)); ++cnt; }
+                int r = q;
+                for (; r + 3 * L0 < P.R; r += 4 * L0) {                  // four loads in flight, added in ascending r
+                    const float v0 = __ldcg(val + r), v1 = __ldcg(val + r + L0), v2 = __ldcg(val + r + 2 * L0), v3 = __ldcg(val + r + 3 * L0);
+                    wsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(wsum, v0), v1), v2), v3);
+                    cnt += 4;
+                }
+                for (; r < P.R; r += L0) { wsum = __fadd_rn(wsum, __ldcg(val + r)); ++cnt; }
                 child_w[lbase + a] = wsum;
                 child_n[lbase + a] = child_n[lbase + a] + cnt;
             }
@@ -367,13 +380,8 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             // adjacent-pairs tree sum of val[0..R): each thread reduces an aligned block of m values in
             // registers / local memory, lanes combine with the xor butterfly (== adjacent pairs, lane i holds
             // block i), warps with a fixed pairing.  Same tree as the oracle for any power-of-two R.
-            constexpr int TS = 512;                                     // threads used by the tree sum (power of two)
-            const int m = P.R >= TS ? P.R / TS : 1;
-            const int nthr = P.R / m;                                   // power of two <= TS
             float v = 0.f;
             if (tid < nthr) {
-                float loc[MAXR / TS];
-                for (int i = 0; i < m; ++i) loc[i] = __ldcg(val + tid * m + i);
                 for (int st = 1; st < m; st <<= 1)
                     for (int i = 0; i < m; i += 2 * st) loc[i] = __fadd_rn(loc[i], loc[i + st]);
                 v = loc[0];

@@ -428,8 +428,11 @@ struct nerrf_sage_session {
     float* bd[64];
     float node_b;
     cudaStream_t st;
+    cudaStream_t cst;               // copy stream: the edge arrays arrive in row-aligned chunks while layer 1 already runs
+    cudaEvent_t ev[8];
     bool has_weights;
 };
+constexpr int SESSION_CHUNKS = 4;
 
 extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, int f_in, int hidden, int num_layers,
                                          nerrf_sage_session** out) {
@@ -456,6 +459,8 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
         F = hidden;
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->cst, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error("session allocation failed: %s", cudaGetErrorString(e));
         nerrf_sage_session_destroy(s);
@@ -489,14 +494,67 @@ extern "C" int nerrf_sage_session_forward_host(nerrf_sage_session* s, const floa
     NERRF_REQUIRE(n_nodes >= 0 && n_nodes <= s->max_nodes && n_edges >= 0 && n_edges <= s->max_edges,
                   "graph (%lld nodes, %lld edges) exceeds the session capacity", (long long)n_nodes, (long long)n_edges);
     if (n_nodes == 0) return NERRF_OK;
-    cudaStream_t st = s->st;
-    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, st));
-    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-    NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
-    int rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
-                                s->node_w, s->node_b, s->h, s->score, s->ws, session_ws_bytes(s->max_nodes, s->max_edges, s->hidden), algo, st);
-    if (rc) return rc;
+    cudaStream_t st = s->st, cst = s->cst;
+    const size_t ws_bytes = session_ws_bytes(s->max_nodes, s->max_edges, s->hidden);
+    int rc;
+    if (s->L >= 2 && n_edges >= (1 << 20)) {
+        // Overlap: x and rowptr first, then col / ew in SESSION_CHUNKS edge-balanced, row-aligned chunks on
+        // the copy stream; layer 1 of a row range starts as soon as its edge chunk has landed.  Layers 2.. need the whole
+        // h_1 and therefore the whole upload, so what can hide is layer 1 (0.6 of the 2.65 ms of compute at cfg 2) under
+        // the edge arrays (80 of the 212 MB); the rest of the step is PCIe time + layers 2..L.
+        int64_t cut[SESSION_CHUNKS + 1];
+        cut[0] = 0; cut[SESSION_CHUNKS] = n_nodes;
+        for (int k = 1; k < SESSION_CHUNKS; ++k) {                   // first row whose edge offset reaches k/C of the edges
+            const int64_t target = n_edges * k / SESSION_CHUNKS;
+            int64_t lo = cut[k - 1], hi = n_nodes;
+            while (lo < hi) { const int64_t mid = (lo + hi) / 2; if ((int64_t)rowptr_host[mid] < target) lo = mid + 1; else hi = mid; }
+            cut[k] = lo;
+        }
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, cst));
+        for (int k = 0; k < SESSION_CHUNKS; ++k) {
+            const int64_t e0 = rowptr_host[cut[k]], e1 = rowptr_host[cut[k + 1]];
+            if (e1 > e0) {
+                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col + e0, col_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
+                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew + e0, ew_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
+            }
+            NERRF_CHECK_CUDA(cudaEventRecord(s->ev[k], cst));
+        }
+        const size_t pp = (((size_t)n_nodes * s->hidden * sizeof(float) + 255) & ~(size_t)255);
+        void* long_ws = ws_bytes > pp + 8192 ? (void*)((unsigned char*)s->ws + pp) : nullptr;
+        const size_t long_ws_bytes = long_ws ? ws_bytes - pp : 0;
+        const float* in = s->x;
+        int F = s->f_in;
+        for (int l = 0; l < s->L; ++l) {
+            float* o = ((s->L - 1 - l) % 2 == 0) ? s->h : s->ws;
+            const bool last = l == s->L - 1;
+            if (l == 0) {
+                for (int k = 0; k < SESSION_CHUNKS; ++k) {
+                    NERRF_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev[k], 0));
+                    if (cut[k + 1] > cut[k]) {
+                        rc = layer_fwd_impl(in, s->rowptr, 0, s->col, s->ew, s->Wd[l], s->bd[l], o, n_nodes, cut[k], cut[k + 1], F, s->hidden, 1,
+                                            algo & 0xFF, nullptr, 0.f, nullptr, long_ws, long_ws_bytes, nullptr, 0, nullptr, st);
+                        if (rc) return rc;
+                    }
+                }
+            } else {
+                rc = layer_fwd_impl(in, s->rowptr, 0, s->col, s->ew, s->Wd[l], s->bd[l], o, n_nodes, 0, n_nodes, F, s->hidden, 1,
+                                    (algo & 0xFF) | (l > 1 ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0), last ? s->node_w : nullptr, s->node_b,
+                                    last ? s->score : nullptr, long_ws, long_ws_bytes, nullptr, 0, nullptr, st);
+                if (rc) return rc;
+            }
+            in = o;
+            F = s->hidden;
+        }
+    } else {
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, st));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
+        rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
+                                s->node_w, s->node_b, s->h, s->score, s->ws, ws_bytes, algo, st);
+        if (rc) return rc;
+    }
     if (score_out_host)
         NERRF_CHECK_CUDA(cudaMemcpyAsync(score_out_host, s->score, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, st));
     if (h_out_host)
@@ -511,6 +569,8 @@ extern "C" int nerrf_sage_session_destroy(nerrf_sage_session* s) {
     cudaFree(s->score); cudaFree(s->node_w);
     for (int l = 0; l < 64; ++l) { if (s->Wd[l]) cudaFree(s->Wd[l]); if (s->bd[l]) cudaFree(s->bd[l]); }
     if (s->st) cudaStreamDestroy(s->st);
+    if (s->cst) cudaStreamDestroy(s->cst);
+    for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     delete s;
     return NERRF_OK;
 }
