@@ -548,11 +548,11 @@ def run_cfg5(dev, dist_rw, n_procs=10400, n_attacked=40):
     model.to(dev); scorer.to(dev)
     t_train = time.perf_counter() - t0
     t0 = time.perf_counter()
-    cols, encrypted = stream.fleet_columns(n_procs, n_attacked, seed=5)
+    cols, encrypted, bad_pids = stream.fleet_columns(n_procs, n_attacked, seed=5, return_pids=True)
     t_gen = time.perf_counter() - t0
     ctx = pipeline.DistContext(dist_rw[0], dist_rw[1]) if dist_rw and dist_rw[1] > 1 else None
     sp = stream.StreamingPlanner(model, scorer, window_s=60.0, tick_s=30.0, top_a=4096, n_rollouts=1024, depth=32, iterations=8,
-                                 commit_per_search=64, device=str(dev), dist_ctx=ctx)
+                                 commit_per_search=64, kill_candidates=True, device=str(dev), dist_ctx=ctx)
     t0 = time.perf_counter()
     ticks = sp.run(cols)
     torch.cuda.synchronize()
@@ -571,7 +571,11 @@ def run_cfg5(dev, dist_rw, n_procs=10400, n_attacked=40):
            "stage_ms_sum_over_ticks": stage, "n_gpus": dist_rw[1] if dist_rw else 1,
            "plan": {"reversions": len(planned), "encrypted_files": len(encrypted), "true_positives": tp,
                     "precision": tp / max(len(planned), 1), "recall": tp / max(len(encrypted), 1),
-                    "exact": planned == encrypted, "truncated_ticks": int(sum(t.truncated for t in ticks))},
+                    "exact": planned == encrypted, "truncated_ticks": int(sum(t.truncated for t in ticks)),
+                    "process_kills": len(sp.killed), "ransomware_processes": len(bad_pids),
+                    "kills_correct": len(sp.killed & bad_pids), "kills_wrong": len(sp.killed - bad_pids),
+                    "note": "planner spec v1: a reversion only sticks once the process that wrote the file is killed (cost 10), so the "
+                            "plan interleaves process kills and file reversions; <= 32 kill candidates per tick"},
            "not_timed": {"train_s": t_train, "trace_generation_s": t_gen},
            "ok": True}
     return out

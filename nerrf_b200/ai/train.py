@@ -69,7 +69,7 @@ def roc_auc(scores, labels) -> float:
 
 
 # ------------------------------------------------------------------ toy set (simulator-schema LockBit traces)
-def make_example(seed: int, n_files: int = 30, benign_files: int = 40) -> dict:
+def make_example(seed: int, n_files: int = 30, benign_files: int = 40, window=None) -> dict:
     """One labelled example: a simulated LockBit trace -> graph tensors + per-file sequences.  Labels: a file node
     is positive iff it was encrypted (graph.graph_from_events meta['label'], from the simulator's annotations).
     Features are OBSERVABLE-ONLY (graph.OBSERVABLE_SLOT): the annotation event kinds that define the label
@@ -78,7 +78,13 @@ def make_example(seed: int, n_files: int = 30, benign_files: int = 40) -> dict:
     What remains is what a wire trace carries: write / rename counts, byte counts, timing, the .lockbit extension
     ("extension pattern", threat-model.mdx:178-184).  The toy set is still easy; see DESIGN.md 2.7."""
     ev = trace_sim.lockbit_trace(n_files=n_files, seed=seed, benign_files=benign_files)
-    g = G.graph_from_events(ev, observable=True)
+    if window is not None:
+        # what the streaming pipeline sees (nerrf_b200.stream): only the events of one sliding window, so a file's
+        # history may start with its encryption and the clock features are relative to the window
+        t_all = [G._parse_ts(e["timestamp"]) for e in ev]
+        lo, hi = t_all[0] + window[0], t_all[0] + window[1]
+        ev = [e for e, t_ in zip(ev, t_all) if lo < t_ <= hi]
+    g = G.graph_from_events(ev, observable=True, window=None if window is None else float(window[1] - window[0]))
     seq, lengths, nodes = pipeline.file_sequences(ev, g, observable=True)
     t = torch.from_numpy
     return {"x": t(g.x), "rowptr": t(g.rowptr), "col": t(g.col), "ew": t(g.ew),
@@ -87,9 +93,21 @@ def make_example(seed: int, n_files: int = 30, benign_files: int = 40) -> dict:
             "graph": g, "events": ev, "seq_nodes": nodes}
 
 
-def toy_set(seeds, **kw):
+def toy_set(seeds, windows: int = 2, **kw):
+    """Per seed: the whole trace plus `windows` random 60 s sliding windows of it (the shape the streamed pipeline feeds
+    the models, docs/content/docs/architecture.mdx:39-41)."""
     rng = np.random.default_rng(1234)
-    return [make_example(int(s), n_files=int(rng.integers(10, 40)), benign_files=int(rng.integers(10, 60)), **kw) for s in seeds]
+    out = []
+    for s in seeds:
+        nf, nb = int(rng.integers(10, 40)), int(rng.integers(10, 60))
+        out.append(make_example(int(s), n_files=nf, benign_files=nb, **kw))
+        span = 3.0 + 0.3 * (nf + nb) + 2.0 + 1.41 * nf                # recon + seeding + encryption phases (trace_sim)
+        for _ in range(windows):
+            hi = float(rng.uniform(0.45, 1.05) * span)
+            ex = make_example(int(s), n_files=nf, benign_files=nb, window=(hi - 60.0, hi), **kw)
+            if ex["seq"].shape[0] > 1 and 0 < float(ex["label"].sum()):
+                out.append(ex)
+    return out
 
 
 def _to(ex, device):

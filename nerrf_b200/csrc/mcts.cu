@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     __shared__ float s_tree[MCTS_WARPS];
     __shared__ int s_arg[MCTS_WARPS];
     __shared__ int s_node, s_depth, s_plen, s_created, s_stop, s_L0, s_numnodes;
+    __shared__ int s_pref[NWORDS];                     // legal actions of the leaf state in the words before word k
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // this CTA's replica of the tree (identical in every CTA: all apply the same deterministic updates)
@@ -310,12 +311,26 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             __syncthreads();
         }
         if (tid == 0) s_L0 = s_L0 - s_depth;                             // legal count of the leaf state
+        if (warp == 1) {                                                 // exclusive prefix of the per-word legal counts (backup)
+            int run = 0;
+            for (int k0 = 0; k0 < NWORDS; k0 += 32) {
+                const int z = __popc(~s_state[k0 + lane]);
+                int inc = z;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t_; }
+                s_pref[k0 + lane] = run + inc - z;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
         __syncthreads();
         const int leaf = s_node, depth = s_depth, L0 = s_L0;
         const bool first_move = (P.D - depth) > 0 && L0 > 0;
         if (prof_on) { const long long c = clock64(); prof[0] += c - tc0; tc0 = c; }
 
         // ------------------------------------------------------------------ rollouts (warp per rollout)
+        // (8 lanes per rollout / 4 rollouts per warp was tried: the per-step chain of dependent collectives got LONGER --
+        // the n-th-set-bit search has to run inside one lane -- and with 7 instead of 28 warps per SM nothing hid it:
+        // 54 k instead of 30 k cycles for the phase, profiles/r02_mcts.md)
         for (int r = (int)blockIdx.x * MCTS_WARPS + warp; r < P.R; r += (int)gridDim.x * MCTS_WARPS) {
             uint32_t w[NW];
 #pragma unroll
@@ -360,8 +375,7 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
                 const uint32_t wv = s_state[a >> 5];
                 if ((wv >> (a & 31)) & 1u) continue;                     // not legal at the leaf
-                int q = __popc(~wv & ((1u << (a & 31)) - 1u));           // zeros below a: in its word ...
-                for (int k = 0; k < (a >> 5); ++k) q += __popc(~s_state[k]);   // ... and in the words before (smem broadcasts)
+                const int q = __popc(~wv & ((1u << (a & 31)) - 1u)) + s_pref[a >> 5];   // legal actions below a
                 if (q >= nq) continue;
                 float wsum = child_w[lbase + a];
                 int cnt = 0;

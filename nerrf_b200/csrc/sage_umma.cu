@@ -399,7 +399,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                        const float* __restrict__ ew, const float* __restrict__ W, const float* __restrict__ bias,
                        float* __restrict__ out, int64_t row_begin, int64_t row_end, int relu,
                        const float* __restrict__ node_w, float node_b, float* __restrict__ score, const LongWs lw,
-                       const Peers peers) {
+                       const Peers peers, unsigned* __restrict__ tile_ctr) {
     using C = UmmaCfg<F, NS>;
     constexpr int K = C::K, LPR = F / 4;
     constexpr int GATHER_WARPS = C::GATHER_WARPS, IDX_STAGES = C::IDX_STAGES;
@@ -417,7 +417,13 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4 + 2 * IDX_STAGES);
     // per gather warp: NQ ring-slot barriers (bulk-copy byte counts), private to the warp
     auto ring_bar = [&](int g, int q) { return bar_base + 256u + 8u * (uint32_t)(g * NQ + q); };
-    static_assert(256 + GATHER_WARPS * NQ * 8 <= 1024, "barrier area");
+    static_assert(256 + GATHER_WARPS * NQ * 8 <= 1024 - 64, "barrier area");
+    // DYNAMIC TILE SCHEDULE: the loader warp claims tiles from a global counter (tile_ctr, zero at launch) and publishes
+    // the id of the CTA's tl-th tile in this ring (-1 = end of stream) before it releases the tile's edge block; every
+    // role reads it after the mbarrier wait that orders it behind that release.  Rows are not equally expensive (hub
+    // destinations: a 32-row tile can hold 50x the edges of an average one), a static round-robin left whole SMs idle.
+    constexpr int TILE_RING = 16;                  // > IDX_STAGES + STAGES + 2 accumulators: an entry outlives its tile
+    volatile int* tile_ids = reinterpret_cast<volatile int*>(smem_gen + (bar_base + 1024 - 64 - smem_base));
     unsigned char* idx_gen = smem_gen + (idx_base - smem_base);
     const uint32_t ring_base = bar_base + 1024;
     float* head_red = reinterpret_cast<float*>(smem_gen + (ring_base - smem_base) + (size_t)GATHER_WARPS * C::RING_BYTES);   // [2][4][32]
@@ -490,8 +496,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES) + (BULK ? 0u : (uint32_t)((grp * F + 4 * sub) * 4));
         const float* xs = x + 4 * sub;
         const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_base - smem_base) + (size_t)g * C::RING_BYTES) + grp * F + 4 * sub;
-        const int tiles_mine = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles in this CTA's sequence
-        const int stream_end = tiles_mine * TN;
+        int stream_end = 0x7fffff00;                                     // rows of this CTA's tile stream; known once the
+                                                                          // end-of-stream entry (-1) shows up
+        int itile = 0, ctile = 0;
 
         // ---- per-row state, issue side (i*) and consume side (c*)
         int ii = g, ib = 0, inb = 1, ie0 = 0, ideg = -1, itl = -1, ilong = -1, iitems = 0;  uint32_t irow = 0;
@@ -505,14 +512,17 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 const int q = tl % IDX_STAGES;
                 mbar_wait(idxf_bar(q), (uint32_t)(tl / IDX_STAGES) & 1u);          // edge block staged
                 itl = tl;
+                itile = tile_ids[tl % TILE_RING];
+                if (itile < 0) stream_end = (tl + 1) * TN;                        // a row-less closing tile: it carries the
+                                                                                  // end of stream through every pipeline
             }
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
             const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
             icol = reinterpret_cast<const int32_t*>(ibp) + rp_s[96 + 2];            // + alignment offset of the col slice
             ielo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
-            const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
+            const int64_t row = row_begin + (int64_t)itile * TN + r;
             ib = 0; inb = 1; ideg = -1;
-            if (row < row_end) {
+            if (itile >= 0 && row < row_end) {
                 irow = (uint32_t)row;
                 ie0 = rp_s[r];
                 ideg = rp_s[r + 1] - ie0;
@@ -527,14 +537,15 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         };
         auto setup_consume_row = [&]() {                                // ci < stream_end, tile already staged
             const int tl = ci / TN, r = ci % TN;
+            if (tl != ctl) ctile = tile_ids[tl % TILE_RING];
             ctl = tl;
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
             const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
             cew = reinterpret_cast<const float*>(ibp + EPAD * 4) + rp_s[96 + 3];    // + alignment offset of the ew slice
             celo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
-            const int64_t row = row_begin + ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TN + r;
+            const int64_t row = row_begin + (int64_t)ctile * TN + r;
             cb = 0; cnb = 1; cdeg = -1;
-            if (row < row_end) {
+            if (ctile >= 0 && row < row_end) {
                 ce0 = rp_s[r];
                 cdeg = rp_s[r + 1] - ce0;
                 citems = cdeg + 1;
@@ -750,14 +761,28 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             }
         };
         int64_t rp[RPW], rp_next[RPW];
-        if ((int64_t)blockIdx.x < n_tiles) load_rp(blockIdx.x, rp);
+        auto claim = [&]() -> int64_t {                                  // next unclaimed tile of the launch (or >= n_tiles)
+            unsigned v = 0;
+            if (lane == 0) v = atomicAdd(tile_ctr, 1u);
+            return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+        };
+        int64_t tile = claim();
+        if (tile < n_tiles) load_rp(tile, rp);
         for (int64_t tl = 0;; ++tl) {
-            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-            if (tile >= n_tiles) break;
-            const bool has_next = tile + gridDim.x < n_tiles;
-            if (has_next) load_rp(tile + gridDim.x, rp_next);           // in flight while we wait for a free stage
+            const bool end = tile >= n_tiles;
+            int64_t next = n_tiles;
+            if (!end) {
+                next = claim();                                          // one tile ahead: its rowptr words are in flight
+                if (next < n_tiles) load_rp(next, rp_next);              // while we wait for a free stage
+            }
             const int q = (int)(tl % IDX_STAGES);
             mbar_wait_relaxed(idxe_bar(q), ((uint32_t)(tl / IDX_STAGES) & 1u) ^ 1u);
+            if (lane == 0) tile_ids[tl % TILE_RING] = end ? -1 : (int)tile;
+            if (end) {                                                   // closing entry: no rows, no edges
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(idxf_bar(q), 0u);
+                break;
+            }
             const int64_t e_lo = __shfl_sync(0xffffffffu, rp[0], 0);
             const int64_t e_hi = __shfl_sync(0xffffffffu, rp[TN / 32], TN % 32);
             unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
@@ -788,14 +813,13 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             }
 #pragma unroll
             for (int k = 0; k < RPW; ++k) rp[k] = rp_next[k];
+            tile = next;
         }
     } else if (warp == MMA_WARP) {
         // =========================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc();
             for (int64_t tl = 0;; ++tl) {
-                const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-                if (tile >= n_tiles) break;
                 const int s = (int)(tl % C::STAGES);
                 const uint32_t n = (uint32_t)(tl / C::STAGES);
                 const int a = (int)(tl & 1);
@@ -803,6 +827,10 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 mbar_wait_relaxed(acce_bar(a), (m & 1u) ^ 1u);           // epilogue drained this accumulator
                 mbar_wait_relaxed(full_bar(s), n & 1u);                  // gather filled this stage
                 tc_fence_after();
+                if (tile_ids[tl % TILE_RING] < 0) {                      // closing entry: hand the end of stream to the epilogue
+                    umma_commit(accf_bar(a));
+                    break;
+                }
                 const uint32_t d_tmem = tmem_base + (uint32_t)(C::ACC_COL0 + a * TN);
                 const uint32_t st0 = smem_base + (uint32_t)(s * C::STAGE_BYTES);
 #pragma unroll 2
@@ -833,12 +861,12 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
         const int f = warp * 32 + lane;
         const float my_nw = node_w ? __ldg(node_w + f) : 0.f;
         for (int64_t tl = 0;; ++tl) {
-            const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-            if (tile >= n_tiles) break;
             const int a = (int)(tl & 1);
             const uint32_t m = (uint32_t)(tl >> 1);
             mbar_wait_relaxed(accf_bar(a), m & 1u);
             tc_fence_after();
+            const int64_t tile = tile_ids[tl % TILE_RING];
+            if (tile < 0) break;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::ACC_COL0 + a * TN);
             const int64_t row0 = row_begin + tile * TN;
             uint32_t v[32];
@@ -916,6 +944,20 @@ inline bool bulk_rows_requested() {
     return v;
 }
 
+// per-device ring of launch-private tile counters (1 KB, allocated on first use and kept): a launch zeroes its slot on its
+// own stream, so launches on different streams do not share a counter unless 256 of them are in flight at once
+inline unsigned* tile_counter_slot(cudaStream_t st) {
+    static unsigned* ring[64] = {};
+    static unsigned next[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    dev_ &= 63;
+    if (!ring[dev_] && cudaMalloc((void**)&ring[dev_], 256 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    unsigned* slot = ring[dev_] + (__atomic_fetch_add(&next[dev_], 1u, __ATOMIC_RELAXED) & 255u);
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) return nullptr;
+    return slot;
+}
+
 template <int F, int NS, typename RP>
 int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const float* ew, const float* W, const float* b,
                 float* out, int64_t row_begin, int64_t row_end, int relu, const float* node_w, float node_b, float* score,
@@ -950,15 +992,17 @@ int launch_umma(const float* x, const RP* rowptr, const int32_t* col, const floa
         if (rc) return rc;
     }
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+    unsigned* tile_ctr = tile_counter_slot(st);
+    if (!tile_ctr) { set_error("could not allocate the tile counter"); return NERRF_ERR_CUDA; }
     // the per-row bulk-copy transport needs 16-byte aligned rows; every transport stages col / ew with bulk copies,
     // which only need 4-byte aligned slices (the aligned superset is copied)
     if (lw.cap > 0)
-        sage_layer_umma_kernel<F, NS, RP, true, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+        sage_layer_umma_kernel<F, NS, RP, true, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers, tile_ctr);
     else if (kBulkVariant<F, NS, RP> && bulk_rows_requested() && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         if constexpr (kBulkVariant<F, NS, RP>)
-            sage_layer_umma_kernel<F, NS, RP, false, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+            sage_layer_umma_kernel<F, NS, RP, false, true><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers, tile_ctr);
     } else
-        sage_layer_umma_kernel<F, NS, RP, false, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers);
+        sage_layer_umma_kernel<F, NS, RP, false, false><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(x, rowptr, col, ew, W, b, out, row_begin, row_end, relu, node_w, node_b, score, lw, peers, tile_ctr);
     return launch_status("sage_layer_umma_kernel");
 }
 

@@ -115,27 +115,31 @@ def _lstm_probs(seq_model, seq_sel, len_sel, dev, ctx):
     return torch.cat(parts)[:a]
 
 
-def process_kill_candidates(g: G.TemporalGraph, candidates: np.ndarray, score, max_kills: int = 32):
+def process_kill_candidates(g: G.TemporalGraph, candidates: np.ndarray, max_kills: int = 32):
     """Non-revert undo candidates derived from the graph (threat-model.mdx:208-222 "Kill process", cost 10): the
-    process nodes that touched the candidate files, most anomalous first.  -> (pid_nodes [k], guard [A] = index into
-    pid_nodes of the process that wrote each candidate file, or -1)."""
-    kind = np.asarray(g.meta["node_kind"])
-    rp = g.rowptr.cpu().numpy() if torch.is_tensor(g.rowptr) else np.asarray(g.rowptr)
-    col = g.col.cpu().numpy() if torch.is_tensor(g.col) else np.asarray(g.col)
-    owner = np.full(candidates.shape[0], -1, np.int64)
-    for i, n in enumerate(candidates.tolist()):              # in-edges of a file node come from the processes that touched it
-        src = col[rp[n]:rp[n + 1]]
-        src = src[kind[src] == 1]
-        if src.size:
-            owner[i] = int(src[-1])                          # the most recent writer
+    process nodes that wrote the candidate files, the ones with the most candidate files first.
+    -> (pid_nodes [k], guard [A] = index into pid_nodes of the process that wrote each candidate file, or -1)."""
+    kind = torch.as_tensor(np.asarray(g.meta["node_kind"]))
+    rp = (g.rowptr.cpu() if torch.is_tensor(g.rowptr) else torch.from_numpy(np.asarray(g.rowptr))).long()
+    col = (g.col.cpu() if torch.is_tensor(g.col) else torch.from_numpy(np.asarray(g.col))).long()
+    cand = torch.from_numpy(np.asarray(candidates, np.int64))
+    # the most recent in-edge of a file node (rows are time-sorted) whose source is a process = its last writer
+    owner = np.full(cand.shape[0], -1, np.int64)
+    last = rp[cand + 1] - 1
+    has = (rp[cand + 1] > rp[cand]).numpy()
+    src = col[last.clamp_min(0)]
+    is_proc = (kind[src] == 1).numpy() & has
+    owner[is_proc] = src.numpy()[is_proc]
+    for i in np.nonzero(has & ~is_proc)[0].tolist():          # rare: the last toucher is a file (rename link): scan back
+        n = int(cand[i]); s_ = col[rp[n]:rp[n + 1]]; s_ = s_[kind[s_] == 1]
+        if s_.numel():
+            owner[i] = int(s_[-1])
     pids, counts = np.unique(owner[owner >= 0], return_counts=True)
     if pids.size == 0:
-        return np.zeros(0, np.int64), np.full(candidates.shape[0], -1, np.int64)
-    sc = score[torch.from_numpy(pids).to(score.device)].cpu().numpy() if torch.is_tensor(score) else np.asarray(score)[pids]
-    order = np.lexsort((pids, -counts, -sc))[:max_kills]
-    chosen = pids[order]
-    slot = {int(p_): k for k, p_ in enumerate(chosen.tolist())}
-    guard = np.asarray([slot.get(int(o), -1) for o in owner.tolist()], np.int64)
+        return np.zeros(0, np.int64), np.full(cand.shape[0], -1, np.int64)
+    chosen = pids[np.lexsort((pids, -counts))[:max_kills]]
+    slot = np.full(int(max(pids.max(), 0)) + 1, -1, np.int64); slot[chosen] = np.arange(chosen.shape[0])
+    guard = np.where(owner >= 0, slot[np.maximum(owner, 0)], -1)
     return chosen, guard
 
 
@@ -198,11 +202,15 @@ def run(g: G.TemporalGraph, seq, lengths, seq_nodes, model: GraphSAGE_T, seq_mod
         p = np.asarray(confidence, np.float32)[cand]
         actions = Actions(p, size_mb, np.ones(a, np.float32))
     elif kill_candidates:
-        pids, guard = process_kill_candidates(g, cand, score)
+        pids, guard = process_kill_candidates(g, cand)
         n_kill = int(pids.shape[0])
         a_rev = min(a, 4096 - n_kill)                                  # kill actions occupy the first slots (spec v1: guards < 32)
         p_rev = 0.5 * (score[candidates[:a_rev]].cpu().numpy() + probs[:a_rev, 0].cpu().numpy())
-        p_all = np.concatenate([score[torch.from_numpy(pids).to(dev)].cpu().numpy(), p_rev]).astype(np.float32)
+        # confidence that a process is malicious = mean confidence of the candidate files it wrote (the model's node head
+        # is trained on file nodes only)
+        gr = guard[:a_rev]
+        p_kill = np.array([p_rev[gr == k].mean() if (gr == k).any() else 0.0 for k in range(n_kill)], np.float32)
+        p_all = np.concatenate([p_kill, p_rev]).astype(np.float32)
         size_all = np.concatenate([np.zeros(n_kill, np.float32), size_mb[:a_rev]])
         kind = np.concatenate([np.full(n_kill, RW_KIND_KILL, np.int64), np.zeros(a_rev, np.int64)])
         cost = np.where(kind == RW_KIND_KILL, 10.0, 1.0).astype(np.float32)

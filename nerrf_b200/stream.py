@@ -80,7 +80,8 @@ def concat_columns(parts) -> ingest.EventColumns:
                                **{k: cat(k) for k in ("ts_sec", "ts_nanos", "pid", "tid", "flags", "ret_val", "bytes", "event_slot", "path_flags")})
 
 
-def fleet_columns(n_procs: int, n_attacked: int, seed: int = 0, n_files: int = 45, benign_files: int = 50, jitter_s: float = 5.0):
+def fleet_columns(n_procs: int, n_attacked: int, seed: int = 0, n_files: int = 45, benign_files: int = 50, jitter_s: float = 5.0,
+                  return_pids: bool = False):
     """A fleet of `n_procs` processes, each with its own n_files + benign_files files under /app/uploads (the m1
     simulator's layout); `n_attacked` of them run the LockBit encryption phase on n_files of their files.
     -> (EventColumns, encrypted_paths: set of the .lockbit3 names a correct plan must rename back)."""
@@ -102,6 +103,8 @@ def fleet_columns(n_procs: int, n_attacked: int, seed: int = 0, n_files: int = 4
         idx = np.nonzero((a.path_flags & 8) != 0)[0]
         raw = data.tobytes()
         enc = {raw[off[i]:off[i + 1]].decode() for i in idx.tolist()}
+    if return_pids:                       # the ransomware processes, by the node name the graph constructor gives them
+        return cols, enc, {"pid:%d" % p_ for p_ in np.unique(parts[0].pid).tolist()} if n_attacked else set()
     return cols, enc
 
 
@@ -139,9 +142,11 @@ class StreamingPlanner:
     depth: int = 32
     iterations: int = 8
     commit_per_search: int = 64
+    kill_candidates: bool = False  # also propose "kill process" actions (planner spec v1: reversions need their writer gone)
     device: str = "cuda"
     dist_ctx: object = None        # pipeline.DistContext for the multi-GPU form
     reverted: set = field(default_factory=set)
+    killed: set = field(default_factory=set)
     ticks: list = field(default_factory=list)
 
     def run(self, cols: ingest.EventColumns):
@@ -166,12 +171,24 @@ class StreamingPlanner:
             lengths = None
             nodes = np.nonzero(np.asarray(g.meta["node_kind"]) == 0)[0]
             names = g.meta["names"]
-            skip = np.asarray([names[n] in self.reverted for n in nodes.tolist()], bool) if self.reverted else None
-            res = pipeline.run(g, seq, lengths, nodes, self.model, self.scorer, top_a=self.top_a, n_rollouts=self.n_rollouts,
-                               depth=self.depth, iterations=self.iterations, device=self.device, exclude=skip,
-                               commit_per_search=self.commit_per_search, dist_ctx=self.dist_ctx)
-            tm.update(res.timings_ms)
-            new = [names[n] for n in res.plan_nodes if names[n] not in self.reverted]
-            self.reverted.update(new)
-            self.ticks.append(TickResult(t_hi - t0, w.n, g.num_nodes, g.num_edges, new, tm, bool(res.plan.truncated)))
+            kind = np.asarray(g.meta["node_kind"])
+            new, truncated = [], False
+            for rnd in range(4):
+                # a planning pass proposes at most 32 process kills (planner spec v1: guards live in state word 0); a tick
+                # with more suspicious processes than that plans again over what is still unreverted
+                skip = np.asarray([names[n] in self.reverted for n in nodes.tolist()], bool) if self.reverted else None
+                res = pipeline.run(g, seq, lengths, nodes, self.model, self.scorer, top_a=self.top_a, n_rollouts=self.n_rollouts,
+                                   depth=self.depth, iterations=self.iterations, device=self.device, exclude=skip,
+                                   commit_per_search=self.commit_per_search, dist_ctx=self.dist_ctx,
+                                   kill_candidates=self.kill_candidates)
+                for k, v in res.timings_ms.items():
+                    tm[k] = tm.get(k, 0.0) + float(v)
+                self.killed.update(names[n] for n in res.plan_nodes if kind[n] == 1)
+                got = [names[n] for n in res.plan_nodes if kind[n] == 0 and names[n] not in self.reverted]
+                self.reverted.update(got)
+                new += got
+                truncated = truncated or bool(res.plan.truncated)
+                if not (self.kill_candidates and res.n_kill >= 32 and got):
+                    break
+            self.ticks.append(TickResult(t_hi - t0, w.n, g.num_nodes, g.num_edges, new, tm, truncated))
         return self.ticks
