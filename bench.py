@@ -415,9 +415,13 @@ def run_multi(args, world, rank, local_rank, dev):
     dist.barrier()
     e2e_s = torch.tensor([(time.perf_counter() - te) / K], device=dev)
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_same = bool(torch.equal(ss.x, x_keep))        # the sharded upload reassembled exactly the resident features
+    # the sharded upload delivered exactly the resident features, on every row this rank reads (own rows + sources of its edges)
+    reads = torch.zeros(N, dtype=torch.bool, device=dev); reads[sh.col.long()] = True; reads[sh.row_begin:sh.row_end] = True
+    ridx = reads.nonzero().squeeze(1)
+    e2e_same = bool(torch.equal(ss.x[ridx], x_keep[ridx]))
+    del reads, ridx
     flag = torch.tensor([int(e2e_same)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    parity["sharded_upload_reassembles_x"] = bool(flag)
+    parity["sharded_upload_delivers_every_row_read"] = bool(flag)
     ok = ok and bool(flag)
     h2d = int(hx_own.numel() * 4 + hrp_own.numel() * hrp_own.element_size() + hcol.numel() * 4 + hew.numel() * 4)
     e2e = {"value": E / float(e2e_s), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(r_loc * 4),

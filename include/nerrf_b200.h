@@ -80,7 +80,7 @@ int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int rowptr_is6
                               nerrf_stream_t stream);
 
 /* Full-option layer call.  node_w == NULL: no fused head.  long_ws (optional device scratch, size from
- * nerrf_sage_long_rows_workspace_bytes): destination rows with more than 512 in-edges ("hub" rows) are
+ * nerrf_sage_long_rows_workspace_bytes): destination rows with more than 128 in-edges ("hub" rows: popular files, process nodes) are
  * pre-aggregated chunk-wise by many CTAs into it instead of being gathered by a single warp; rows that do
  * not fit in the scratch (or long_ws == NULL) are processed inline -- same result, slower. */
 int nerrf_sage_long_rows_workspace_bytes(int64_t n_edges, size_t* bytes);

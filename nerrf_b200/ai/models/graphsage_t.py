@@ -140,13 +140,13 @@ class GraphSAGE_T(nn.Module):
         return out
 
     def _has_hub_rows(self, rowptr) -> bool:
-        """Graph metadata (max in-degree > 512?), computed once per rowptr tensor (one device sync) and cached.
+        """Graph metadata (max in-degree > 128: the kernel's long-row threshold), computed once per rowptr tensor (one device sync) and cached.
         A stale cache entry can only cost speed, never correctness: without the scratch hub rows are
         processed inline, with it the pre-pass simply finds nothing."""
         key = (rowptr.data_ptr(), rowptr.numel(), rowptr._version)
         if getattr(self, "_hub_key", None) != key:
             self._hub_key = key
-            self._hub_val = bool((rowptr[1:] - rowptr[:-1]).max() > 512) if rowptr.numel() > 1 else False
+            self._hub_val = bool((rowptr[1:] - rowptr[:-1]).max() > 128) if rowptr.numel() > 1 else False
         return self._hub_val
 
     def _long_rows_ws(self, n_edges, device):

@@ -330,8 +330,9 @@ extern "C" int nerrf_sage_layer_head_fwd(const float* x, const void* rowptr, int
 
 extern "C" int nerrf_sage_long_rows_workspace_bytes(int64_t n_edges, size_t* bytes) {
     NERRF_REQUIRE(bytes && n_edges >= 0, "bad argument");
-    // every 512-edge chunk of a hub row + one spare chunk per hub row (<= n_edges/512 of them); 560 B per chunk item
-    const int64_t items = 2 * (n_edges / 512) + 64;
+    // rows with more than 128 in-edges are cut into 256-edge chunks: <= n_edges/256 full chunks + one partial chunk per
+    // such row (<= n_edges/128 rows); 560 B per chunk item.  Capacity driven: what does not fit is processed inline.
+    const int64_t items = 3 * (n_edges / 256) + 64;
     *bytes = (size_t)items * 560 + 8192;
     return NERRF_OK;
 }

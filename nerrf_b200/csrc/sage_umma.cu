@@ -278,8 +278,12 @@ __device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, 
 // weighted sum + weight sum (fixed order: 8 warps x 64 edges, then warp 0 adds the 8 warp partials in order)
 // into a side buffer.  The main kernel then sees the row as the items [self, partial_0 .. partial_{nc-1}]
 // (weight 1 each, weight-sum from pw[]).  The workspace is capacity driven: rows that do not fit stay inline.
-constexpr int LONG_T = 512;            // == EMAX: such a row can never be fully staged anyway
-constexpr int LONG_CH = 512;
+// Threshold: a 300-edge row gathered by one warp (512 B per edge at ~6 GB/s per warp) takes ~25 us while the other 31 rows
+// of its tile are done in 2 -- and a trace graph has exactly such a row every 64 nodes (the process node of each
+// component, in-degree = events of its files).  Measured on the trace-structured bench graph: 2.07 ms per F=128 layer with
+// the r1 threshold of 512, see profiles/r02_bench_n2.json vs r02 final.
+constexpr int LONG_T = 128;
+constexpr int LONG_CH = 256;
 
 struct LongWs {
     int* hdr;              // [0] = number of chunk items claimed (may exceed cap), [1] = cap
@@ -565,7 +569,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                     const int nitems = iitems - first;                   // items left in the row (>= 1)
                     const uint32_t dst = ring_u32 + (uint32_t)(slot * SLOT_FLOATS * 4);
                     const int kbase = ie0 + first - 1;                   // item `it` of this sub-batch is edge kbase + it
-                    if (ie0 + ideg <= EMAX) {                            // whole row staged (the common case): branch free
+                    if (!(LONG && ilong >= 0) && ie0 + ideg <= EMAX) {   // whole row staged (the common case): branch free
                         uint32_t src[QS / G];
 #pragma unroll
                         for (int t = 0; t < QS; t += G) src[t / G] = (uint32_t)icol[kbase + t + grp];   // slack reads stay in smem
@@ -659,7 +663,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 const int nitems = citems - first;
                 const float* rs = ring_gen + cslot * SLOT_FLOATS;
                 const int kbase = ce0 + first - 1;
-                if (ce0 + cdeg <= EMAX) {                                // whole row staged: batched LDS, predicated math
+                if (!(LONG && clong >= 0) && ce0 + cdeg <= EMAX) {       // whole row staged: batched LDS, predicated math
                     float4 v[QS / G];
                     float w[QS / G];
 #pragma unroll

@@ -82,7 +82,8 @@ class DistContext:
     seed + r, root statistics summed in rank order) -- every rank ends with the same plan."""
     rank: int
     world: int
-    exchange: str = "p2p"
+    exchange: str = "broadcast"      # NCCL all-gather-v per layer: window graphs change size every tick, so the peer-mapped
+                                     # buffers of the fused exchange (sized by N, collectively allocated) would be rebuilt per tick
 
 
 def _sage_scores(g_dev, model, ctx):

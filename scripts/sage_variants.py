@@ -12,8 +12,13 @@ N, E = 1_000_000, 10_000_000
 model = GraphSAGE_T(32, 128, 3).to(dev)
 ref = GraphSAGE_T(32, 128, 3, algo="ffma").to(dev)
 out = {}
-for fam in ("hub_src", "hub_dst", "uniform"):
-    rp, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, family=fam)
+from nerrf_b200.dist import gpu_trace_graph
+for fam in ("hub_src", "hub_dst", "uniform", "trace"):
+    if fam == "trace":
+        rp, col, ew, x, _ = gpu_trace_graph(15625, dev)
+        N, E = rp.numel() - 1, col.numel()
+    else:
+        rp, col, ew, x = gpu_synthetic_graph(N, E, 20250115, dev, family=fam)
     bufs = [torch.empty(N, 128, device=dev) for _ in range(2)]
     score = torch.empty(N, device=dev)
     def step(ev=None):

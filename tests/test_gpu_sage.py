@@ -225,7 +225,7 @@ def test_fused_head_matches_separate_head(algo):
 
 @pytest.mark.parametrize("F", [32, 128])
 def test_hub_rows_preaggregated_path_matches_inline_and_oracle(F):
-    """Rows with > 512 in-edges take the chunk pre-aggregation path; same answer as the inline path and the oracle."""
+    """Rows with > 128 in-edges take the chunk pre-aggregation path; same answer as the inline path and the oracle."""
     rng = np.random.default_rng(F)
     N, E = 4000, 120000
     dst = np.minimum((N * rng.random(E) ** 6).astype(np.int64), N - 1)          # a few rows with 10^3..10^4 in-edges
