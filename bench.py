@@ -124,6 +124,8 @@ def oracle_check(model, rowptr, col, ew, x, h_gpu, score_gpu, k=64):
     """The C/OpenMP oracle (oracle/c/sage_oracle.c) over the FULL graph on the host cores vs a GPU forward: every element
     of h, every score, the top-k anomalous-node ranking.  The oracle is the checker here, never the product path."""
     from oracle import c_sage
+    # torchrun exports OMP_NUM_THREADS=1: give the checker the cores the box grants (cgroup quota: 16 of the 128 logical CPUs)
+    c_sage.set_threads(min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     t0 = time.perf_counter()
     hw, sw = c_sage.forward(model.oracle_params(), x.cpu().numpy(), rowptr.cpu().numpy(), col.cpu().numpy(), ew.cpu().numpy())
     dt = time.perf_counter() - t0
