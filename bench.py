@@ -547,22 +547,31 @@ def run_cfg5(dev, dist_rw, n_procs=10400, n_attacked=40):
     from nerrf_b200.ai import train as T
     from nerrf_b200.ai.models import GraphSAGE_T
     from nerrf_b200.ai.models.lstm import LSTMScorer
+    multi = bool(dist_rw and dist_rw[1] > 1)
+    lead = not multi or dist_rw[0] == 0
     t0 = time.perf_counter()
     torch.manual_seed(0)
     model, scorer = GraphSAGE_T(F_IN, HIDDEN, 2), LSTMScorer()
-    T.train(model, scorer, T.toy_set(range(100, 104)), epochs=25, lr=3e-3)           # ai/train.py, CPU autograd (not timed)
+    if lead:                                                       # ai/train.py, CPU autograd (not timed); N>1: rank 0 trains,
+        T.train(model, scorer, T.toy_set(range(100, 104)), epochs=25, lr=3e-3)        # the weights are broadcast
     model.to(dev); scorer.to(dev)
+    if multi:
+        import torch.distributed as dist
+        for p_ in list(model.parameters()) + list(scorer.parameters()):
+            dist.broadcast(p_.data, 0)
     t_train = time.perf_counter() - t0
     t0 = time.perf_counter()
-    cols, encrypted, bad_pids = stream.fleet_columns(n_procs, n_attacked, seed=5, return_pids=True)
+    cols, encrypted, bad_pids = stream.fleet_columns(n_procs, n_attacked, seed=5, return_pids=True) if lead else (None, set(), set())
     t_gen = time.perf_counter() - t0
-    ctx = pipeline.DistContext(dist_rw[0], dist_rw[1]) if dist_rw and dist_rw[1] > 1 else None
+    ctx = pipeline.DistContext(dist_rw[0], dist_rw[1]) if multi else None
     sp = stream.StreamingPlanner(model, scorer, window_s=60.0, tick_s=30.0, top_a=4096, n_rollouts=1024, depth=32, iterations=8,
                                  commit_per_search=64, kill_candidates=True, device=str(dev), dist_ctx=ctx)
     t0 = time.perf_counter()
     ticks = sp.run(cols)
     torch.cuda.synchronize()
     t_run = time.perf_counter() - t0
+    if not lead:                                                   # the plan (names) lives on rank 0
+        return {"ok": True}
     planned = set(sp.reverted)
     tp = len(planned & encrypted)
     big = max(ticks, key=lambda t: t.nodes)
@@ -571,7 +580,8 @@ def run_cfg5(dev, dist_rw, n_procs=10400, n_attacked=40):
         for k, v in t.timings_ms.items():
             stage[k] = stage.get(k, 0.0) + float(v)
     out = {"workload": f"fleet trace: {n_procs} processes x 95 files (m1 simulator schema), {n_attacked} ransomware processes x 45 encrypted "
-                       f"files; 60 s sliding window, one tick per 30 s of trace time",
+                       f"files; 60 s sliding window, one tick per 30 s of trace time" +
+                       ("; host-side ingest on rank 0, device graph / sequences broadcast, GNN sharded, LSTM batch split, MCTS root-parallel" if multi else ""),
            "events": int(cols.n), "events_per_s_end_to_end": cols.n / t_run, "ticks": len(ticks), "seconds_total": t_run,
            "largest_window": {"events": big.events, "nodes": big.nodes, "edges": big.edges, "timings_ms": {k: float(v) for k, v in big.timings_ms.items()}},
            "stage_ms_sum_over_ticks": stage, "n_gpus": dist_rw[1] if dist_rw else 1,

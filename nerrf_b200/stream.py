@@ -150,45 +150,105 @@ class StreamingPlanner:
     ticks: list = field(default_factory=list)
 
     def run(self, cols: ingest.EventColumns):
+        """cols: the event stream (multi-GPU: only rank 0's copy is read -- rank 0 does the host-side ingest of every tick
+        and broadcasts the device graph, the exclusion mask and the candidates' sequences; names stay on rank 0)."""
         from . import pipeline
         import time
-        ts = cols.timestamp
-        t0, t1 = float(ts.min()), float(ts.max())
+        import torch
+        ctx = self.dist_ctx
+        multi = ctx is not None and ctx.world > 1
+        lead = not multi or ctx.rank == 0
+        dev = torch.device(self.device)
+        if multi:
+            import torch.distributed as dist
+
+            def bcast(t, shape=None, dtype=None):
+                """broadcast a tensor from rank 0 (shape / dtype known to everybody, or sent first)"""
+                if shape is None:
+                    hdr = torch.tensor(list(t.shape) + [-1] * (4 - t.dim()) if lead else [0] * 4, device=dev, dtype=torch.int64)
+                    dist.broadcast(hdr, 0)
+                    shape = [int(v) for v in hdr.tolist() if v >= 0]
+                buf = t.to(dev).contiguous() if lead else torch.empty(shape, device=dev, dtype=dtype)
+                dist.broadcast(buf, 0)
+                return buf
+        if lead:
+            ts = cols.timestamp
+            span = torch.tensor([float(ts.min()), float(ts.max())], dtype=torch.float64, device=dev)
+        else:
+            span = torch.zeros(2, dtype=torch.float64, device=dev)
+        if multi:
+            dist.broadcast(span, 0)
+        t0, t1 = float(span[0]), float(span[1])
         t_hi = t0
         while t_hi < t1:
             t_hi = min(t_hi + self.tick_s, t1)
             tm = {}
-            a = time.perf_counter()
-            w = window(cols, t_hi - self.window_s, t_hi)
-            tm["window"] = (time.perf_counter() - a) * 1e3
-            if w.n == 0:
+            names, w, n_events = None, None, 0
+            if lead:
+                a = time.perf_counter()
+                w = window(cols, t_hi - self.window_s, t_hi)
+                tm["window"] = (time.perf_counter() - a) * 1e3
+                n_events = w.n
+            if multi:
+                ne = torch.tensor([n_events], device=dev); dist.broadcast(ne, 0); n_events = int(ne)
+            if n_events == 0:
                 continue
             a = time.perf_counter()
-            g = ingest.graph_from_columns(w, device=self.device, observable=True, window=self.window_s)
+            if lead:
+                g = ingest.graph_from_columns(w, device=self.device, observable=True, window=self.window_s)
+                names = g.meta["names"]
+            if multi:                                      # the device graph travels over NVLink; the strings do not
+                x = bcast(g.x if lead else None, dtype=torch.float32)
+                rp = bcast(g.rowptr.to(torch.int64) if lead else None, dtype=torch.int64).to(torch.int32)
+                col = bcast(g.col if lead else None, dtype=torch.int32)
+                ew = bcast(g.ew if lead else None, dtype=torch.float32)
+                kind_t = bcast(torch.from_numpy(np.asarray(g.meta["node_kind"]).astype(np.int64)) if lead else None, dtype=torch.int64)
+                size_t = bcast(torch.from_numpy(np.asarray(g.meta["size_mb"], np.float32)) if lead else None, dtype=torch.float32)
+                if not lead:
+                    g = G.TemporalGraph(rp, col, ew, x, {"kind": "trace", "node_kind": kind_t.cpu().numpy(), "size_mb": size_t.cpu().numpy()})
             tm["graph_build"] = (time.perf_counter() - a) * 1e3
-            # LSTM sequences are built lazily, for the top-A candidates only (a window holds ~10^6 file nodes)
-            seq = lambda cand, w=w: ingest.sequences_from_columns(w, observable=True, only_nodes=cand)
-            lengths = None
-            nodes = np.nonzero(np.asarray(g.meta["node_kind"]) == 0)[0]
-            names = g.meta["names"]
             kind = np.asarray(g.meta["node_kind"])
+            nodes = np.nonzero(kind == 0)[0]
+
+            # LSTM sequences are built lazily, for the top-A candidates only (a window holds ~10^6 file nodes)
+            def seq(cand, w=w):
+                if lead:
+                    sq, ln, have = ingest.sequences_from_columns(w, observable=True, only_nodes=cand)
+                if multi:
+                    sq_t = bcast(torch.from_numpy(sq) if lead else None, dtype=torch.float32)
+                    ln_t = bcast(torch.from_numpy(ln) if lead else None, dtype=torch.int32)
+                    hv_t = bcast(torch.from_numpy(have) if lead else None, dtype=torch.int64)
+                    return sq_t.cpu().numpy(), ln_t.cpu().numpy(), hv_t.cpu().numpy()
+                return sq, ln, have
+
             new, truncated = [], False
             for rnd in range(4):
                 # a planning pass proposes at most 32 process kills (planner spec v1: guards live in state word 0); a tick
                 # with more suspicious processes than that plans again over what is still unreverted
-                skip = np.asarray([names[n] in self.reverted for n in nodes.tolist()], bool) if self.reverted else None
-                res = pipeline.run(g, seq, lengths, nodes, self.model, self.scorer, top_a=self.top_a, n_rollouts=self.n_rollouts,
+                skip = None
+                if lead and self.reverted:
+                    skip = np.asarray([names[n] in self.reverted for n in nodes.tolist()], bool)
+                if multi:
+                    flag = torch.tensor([1 if (lead and skip is not None) else 0], device=dev); dist.broadcast(flag, 0)
+                    if int(flag):
+                        skip = bcast(torch.from_numpy(skip) if lead else None, shape=[nodes.shape[0]], dtype=torch.bool).cpu().numpy()
+                res = pipeline.run(g, seq, None, nodes, self.model, self.scorer, top_a=self.top_a, n_rollouts=self.n_rollouts,
                                    depth=self.depth, iterations=self.iterations, device=self.device, exclude=skip,
                                    commit_per_search=self.commit_per_search, dist_ctx=self.dist_ctx,
                                    kill_candidates=self.kill_candidates)
                 for k, v in res.timings_ms.items():
                     tm[k] = tm.get(k, 0.0) + float(v)
-                self.killed.update(names[n] for n in res.plan_nodes if kind[n] == 1)
-                got = [names[n] for n in res.plan_nodes if kind[n] == 0 and names[n] not in self.reverted]
-                self.reverted.update(got)
-                new += got
+                got = []
+                if lead:
+                    self.killed.update(names[n] for n in res.plan_nodes if kind[n] == 1)
+                    got = [names[n] for n in res.plan_nodes if kind[n] == 0 and names[n] not in self.reverted]
+                    self.reverted.update(got)
+                    new += got
+                more = bool(self.kill_candidates and res.n_kill >= 32 and got)
+                if multi:
+                    flag = torch.tensor([int(more)], device=dev); dist.broadcast(flag, 0); more = bool(int(flag))
                 truncated = truncated or bool(res.plan.truncated)
-                if not (self.kill_candidates and res.n_kill >= 32 and got):
+                if not more:
                     break
-            self.ticks.append(TickResult(t_hi - t0, w.n, g.num_nodes, g.num_edges, new, tm, truncated))
+            self.ticks.append(TickResult(t_hi - t0, n_events, g.num_nodes, g.num_edges, new, tm, truncated))
         return self.ticks

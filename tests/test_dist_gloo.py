@@ -77,3 +77,46 @@ def test_sharded_forward_matches_single_process(world, exchange):
     assert all(r[1] for r in res), res
     assert res[0][2] == 0 and res[-1][3] == 3000 and all(a[3] == b[2] for a, b in zip(res, res[1:]))
     assert len({r[4] for r in res}) == 1            # bit-identical merged MCTS value sums on every rank
+
+
+def _worker_pipeline_pieces(rank, world, port, q):
+    """Host-side logic of the multi-GPU pipeline (pipeline.DistContext) under gloo: the LSTM batch split + all-gather
+    returns exactly the unsplit result in the original order; component-aligned cuts never split a component."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerrf_b200 import pipeline
+        ctx = pipeline.DistContext(rank, world)
+        rng = np.random.default_rng(3)
+        seq = rng.standard_normal((37, 5, 4)).astype(np.float32); ln = rng.integers(0, 6, 37).astype(np.int32)
+        model = lambda s, l: torch.stack([s.sum((1, 2)), l.float()], 1)          # any per-row function
+        got = pipeline._lstm_probs(model, seq, ln, torch.device("cpu"), ctx)
+        want = model(torch.from_numpy(seq), torch.from_numpy(ln))
+        ok = torch.equal(got, want)
+        tiny = pipeline._lstm_probs(model, seq[:1], ln[:1], torch.device("cpu"), ctx)   # fewer rows than ranks: no split
+        ok = ok and torch.equal(tiny, want[:1])
+        # component-aligned cuts: 50 components of 64 nodes, uneven edges per component
+        S, K = 64, 50
+        deg = np.repeat(rng.integers(1, 30, K), S)
+        rowptr = np.zeros(S * K + 1, np.int64); np.cumsum(deg, out=rowptr[1:])
+        col = np.zeros(int(rowptr[-1]), np.int32); ew = np.ones(int(rowptr[-1]), np.float32)
+        sh = ND.Shard(rowptr, col, ew, rank, world, align=S)
+        ok = ok and all(int(c) % S == 0 for c in sh.cuts) and sh.cuts[0] == 0 and sh.cuts[-1] == S * K
+        ok = ok and all(b >= a for a, b in zip(sh.cuts, sh.cuts[1:]))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_batch_split_and_component_aligned_cuts():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 91
+    procs = [ctx.Process(target=_worker_pipeline_pieces, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
