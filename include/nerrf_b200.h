@@ -118,6 +118,22 @@ int nerrf_sage_forward(const float* x, const void* rowptr, int rowptr_is64, cons
                        float node_b, float* h_out, float* score_out, float* workspace,
                        size_t workspace_bytes, int algo, nerrf_stream_t stream);
 
+/* ------------------------------------------------------------------ GraphSAGE-T layer backward (training)
+ * Replaces: the GraphSAGE-T half of ai/train.py "joint GNN+LSTM training script" (README.md:75; ROADMAP.md:62-69).
+ * Given one layer's saved tensors -- input h_in [n,F], its aggregate m [n,F] (nerrf_sage_aggregate of h_in), output
+ * y [n,H] -- and the gradient dy [n,H] of the loss w.r.t. y:
+ *     dP = dy * [y > 0] (relu != 0) or dy;   db = sum_v dP[v];   dW = [h_in || m]^T dP  ([2F,H]);
+ *     dZ = dP W^T;   dh = dZ[:, :F] + A^T dZ[:, F:]
+ * A^T is a gather over the TRANSPOSED graph, CSR by source: t_rowptr [n+1], t_col [E] = destination of each out-edge,
+ * t_w [E] = ew_e / max(weight sum of that destination, 1e-12).  dh == NULL skips the input gradient (first layer),
+ * dW == NULL (with db) skips the weight gradient.  fp32, no atomics: bit-reproducible.  All pointers device,
+ * 16-byte aligned; workspace from nerrf_sage_layer_bwd_workspace_bytes. */
+int nerrf_sage_layer_bwd_workspace_bytes(int64_t n_nodes, int F, size_t* bytes);
+int nerrf_sage_layer_bwd(const float* h_in, const float* m, const float* y, const float* dy, const float* W,
+                         const void* t_rowptr, int t_rowptr_is64, const int32_t* t_col, const float* t_w,
+                         float* dh, float* dW, float* db, float* workspace, size_t workspace_bytes,
+                         int64_t n_nodes, int F, int H, int relu, nerrf_stream_t stream);
+
 /* Host-buffer session (the e2e call): device buffers live in the handle. */
 typedef struct nerrf_sage_session nerrf_sage_session;
 int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, int f_in, int hidden,
@@ -131,6 +147,17 @@ int nerrf_sage_session_forward_host(nerrf_sage_session* s, const float* x_host,
                                     const int32_t* rowptr_host, const int32_t* col_host,
                                     const float* ew_host, int64_t n_nodes, int64_t n_edges,
                                     float* score_out_host, float* h_out_host, int algo);
+/* Pipelined form of the same call (a stream of graphs, e.g. one per sliding-window tick): submit queues H2D -> forward ->
+ * D2H on the session's streams and returns at once with a ticket; wait blocks until that ticket's outputs are in the
+ * host buffers.  Two steps may be in flight (two device buffer sets): the upload of step i+1 overlaps the layers of
+ * step i.  A third submit blocks until the oldest ticket is complete.  The host buffers of a ticket must stay valid and
+ * unmodified until its wait returns.  forward_host == submit + wait. */
+int nerrf_sage_session_submit_host(nerrf_sage_session* s, const float* x_host,
+                                   const int32_t* rowptr_host, const int32_t* col_host,
+                                   const float* ew_host, int64_t n_nodes, int64_t n_edges,
+                                   float* score_out_host, float* h_out_host, int algo,
+                                   uint64_t* ticket);
+int nerrf_sage_session_wait(nerrf_sage_session* s, uint64_t ticket);
 int nerrf_sage_session_destroy(nerrf_sage_session* s);
 
 /* ------------------------------------------------------------------ rewards.score (row a6)

@@ -28,6 +28,9 @@ SIGNATURES = {
                                        C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "nerrf_sage_layer_head_fwd": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64,
                                             C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp]),
+    "nerrf_sage_layer_bwd_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
+    "nerrf_sage_layer_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int64, C.c_int,
+                                       C.c_int, C.c_int, vp]),
     "nerrf_sage_long_rows_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "nerrf_sage_layer_fwd_ex": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64,
                                           C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp, C.c_size_t,
@@ -39,6 +42,8 @@ SIGNATURES = {
     "nerrf_sage_session_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "nerrf_sage_session_set_weights": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_float]),
     "nerrf_sage_session_forward_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int]),
+    "nerrf_sage_session_submit_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, C.POINTER(C.c_uint64)]),
+    "nerrf_sage_session_wait": (C.c_int, [vp, C.c_uint64]),
     "nerrf_sage_session_destroy": (C.c_int, [vp]),
     "nerrf_reward_score": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, C.c_int, vp, vp]),
     "nerrf_mcts_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),

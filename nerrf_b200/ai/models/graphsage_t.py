@@ -213,6 +213,7 @@ class HostSession:
         import ctypes as C
         self.model = model
         self._h = C.c_void_p()
+        self._inflight = {}
         L.check(L.lib().nerrf_sage_session_create(max_nodes, max_edges, model.in_dim, model.hidden, model.num_layers,
                                                   C.byref(self._h)), "nerrf_sage_session_create")
         Ws = [w.detach().cpu().contiguous() for w in model.weights]
@@ -233,6 +234,32 @@ class HostSession:
                                                         x.shape[0], col.numel(), L.ptr(score_out), L.ptr(h_out), algo),
                 "nerrf_sage_session_forward_host")
         return score_out
+
+    def submit(self, x, rowptr, col, edge_w, score_out, h_out=None) -> int:
+        """Pipelined form (`nerrf_sage_session_submit_host`): queue the step and return a ticket at once; up to two
+        steps are in flight, the upload of one overlapping the layers of the other.  The host tensors must stay alive and
+        unmodified until `wait(ticket)` returns -- the session keeps references to them until then."""
+        import ctypes as C
+        for t in (x, rowptr, col, edge_w, score_out):
+            if t.is_cuda:
+                raise L.NerrfError("HostSession takes host tensors")
+        if rowptr.dtype != torch.int32:
+            raise TypeError("host session uses int32 rowptr")
+        ticket = C.c_uint64(0)
+        L.check(L.lib().nerrf_sage_session_submit_host(self._h, L.ptr(x), L.ptr(rowptr), L.ptr(col), L.ptr(edge_w),
+                                                       x.shape[0], col.numel(), L.ptr(score_out), L.ptr(h_out),
+                                                       ALGOS[self.model.algo], C.byref(ticket)),
+                "nerrf_sage_session_submit_host")
+        self._inflight[ticket.value] = (x, rowptr, col, edge_w, score_out, h_out)
+        return ticket.value
+
+    def wait(self, ticket: int):
+        """Block until the outputs of `ticket` are in its host tensors; returns its score tensor."""
+        L.check(L.lib().nerrf_sage_session_wait(self._h, int(ticket)), "nerrf_sage_session_wait")
+        held = self._inflight.pop(int(ticket), None)
+        for t in [k for k in self._inflight if k < int(ticket) - 1]:      # older tickets completed when their slot was reused
+            self._inflight.pop(t, None)
+        return held[4] if held else None
 
     def close(self):
         if self._h:

@@ -420,20 +420,27 @@ static size_t session_ws_bytes(int64_t max_nodes, int64_t max_edges, int hidden)
     return (((size_t)max_nodes * hidden * 4 + 255) & ~(size_t)255) + lb;
 }
 
+constexpr int SESSION_CHUNKS = 4;
+constexpr int SESSION_SLOTS = 2;      // input / score buffer sets: the upload of step i+1 runs under the compute of step i
+
 struct nerrf_sage_session {
     int64_t max_nodes, max_edges;
     int f_in, hidden, L;
-    float *x, *ew, *h, *ws, *score, *node_w;
-    int32_t *rowptr, *col;
+    float *x[SESSION_SLOTS], *ew[SESSION_SLOTS], *score[SESSION_SLOTS];
+    int32_t *rowptr[SESSION_SLOTS], *col[SESSION_SLOTS];
+    float *h, *ws, *node_w;         // activations: one set (the compute of consecutive steps is serial on `st`)
     float* Wd[64];
     float* bd[64];
     float node_b;
-    cudaStream_t st;
-    cudaStream_t cst;               // copy stream: the edge arrays arrive in row-aligned chunks while layer 1 already runs
-    cudaEvent_t ev[8];
+    cudaStream_t st;                // compute
+    cudaStream_t cst;               // H2D: the edge arrays arrive in row-aligned chunks while layer 1 already runs
+    cudaStream_t dst;               // D2H of the scores (PCIe is full duplex: it runs under the next step's upload)
+    cudaEvent_t ev[SESSION_SLOTS][SESSION_CHUNKS];
+    cudaEvent_t compute_done[SESSION_SLOTS], out_done[SESSION_SLOTS];
+    uint64_t next_ticket;           // tickets are 1, 2, ...; ticket t uses slot t % SESSION_SLOTS
+    uint64_t slot_ticket[SESSION_SLOTS];   // ticket whose work is (or was last) queued on the slot, 0 = none
     bool has_weights;
 };
-constexpr int SESSION_CHUNKS = 4;
 
 extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, int f_in, int hidden, int num_layers,
                                          nerrf_sage_session** out) {
@@ -445,13 +452,15 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
     s->max_nodes = max_nodes; s->max_edges = max_edges; s->f_in = f_in; s->hidden = hidden; s->L = num_layers;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 16); };
-    A((void**)&s->x, (size_t)max_nodes * f_in * 4);
-    A((void**)&s->rowptr, (size_t)(max_nodes + 1) * 4);
-    A((void**)&s->col, (size_t)max_edges * 4);
-    A((void**)&s->ew, (size_t)max_edges * 4);
+    for (int k = 0; k < SESSION_SLOTS; ++k) {
+        A((void**)&s->x[k], (size_t)max_nodes * f_in * 4);
+        A((void**)&s->rowptr[k], (size_t)(max_nodes + 1) * 4);
+        A((void**)&s->col[k], (size_t)max_edges * 4);
+        A((void**)&s->ew[k], (size_t)max_edges * 4);
+        A((void**)&s->score[k], (size_t)max_nodes * 4);
+    }
     A((void**)&s->h, (size_t)max_nodes * hidden * 4);
     A((void**)&s->ws, session_ws_bytes(max_nodes, max_edges, hidden));
-    A((void**)&s->score, (size_t)max_nodes * 4);
     A((void**)&s->node_w, (size_t)hidden * 4);
     int F = f_in;
     for (int l = 0; l < num_layers; ++l) {
@@ -461,7 +470,12 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->cst, cudaStreamNonBlocking);
-    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->dst, cudaStreamNonBlocking);
+    for (int k = 0; k < SESSION_SLOTS; ++k) {
+        for (int i = 0; i < SESSION_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev[k][i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->compute_done[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->out_done[k], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         set_error("session allocation failed: %s", cudaGetErrorString(e));
         nerrf_sage_session_destroy(s);
@@ -474,6 +488,7 @@ extern "C" int nerrf_sage_session_create(int64_t max_nodes, int64_t max_edges, i
 extern "C" int nerrf_sage_session_set_weights(nerrf_sage_session* s, const float* const* W, const float* const* b,
                                               const float* node_w, float node_b) {
     NERRF_REQUIRE(s && W && b && node_w, "null pointer");
+    NERRF_CHECK_CUDA(cudaStreamSynchronize(s->st));                  // steps in flight read the old weights
     int F = s->f_in;
     for (int l = 0; l < s->L; ++l) {
         NERRF_CHECK_CUDA(cudaMemcpyAsync(s->Wd[l], W[l], (size_t)2 * F * s->hidden * 4, cudaMemcpyHostToDevice, s->st));
@@ -487,91 +502,138 @@ extern "C" int nerrf_sage_session_set_weights(nerrf_sage_session* s, const float
     return NERRF_OK;
 }
 
-extern "C" int nerrf_sage_session_forward_host(nerrf_sage_session* s, const float* x_host, const int32_t* rowptr_host,
-                                               const int32_t* col_host, const float* ew_host, int64_t n_nodes,
-                                               int64_t n_edges, float* score_out_host, float* h_out_host, int algo) {
-    NERRF_REQUIRE(s && x_host && rowptr_host && col_host && ew_host, "null pointer");
+// Queue one step: H2D of the graph (copy stream) -> forward (compute stream) -> D2H of the scores (third stream), all
+// asynchronous.  Two buffer sets: the upload of ticket t+1 overlaps the layers of ticket t, whose score read-back
+// overlaps both -- the steady state of a stream of graphs (one per sliding-window tick) is bounded by PCIe H2D time
+// alone.  The host buffers of a ticket must stay valid and unmodified until nerrf_sage_session_wait(ticket) returns.
+extern "C" int nerrf_sage_session_submit_host(nerrf_sage_session* s, const float* x_host, const int32_t* rowptr_host,
+                                              const int32_t* col_host, const float* ew_host, int64_t n_nodes,
+                                              int64_t n_edges, float* score_out_host, float* h_out_host, int algo,
+                                              uint64_t* ticket) {
+    NERRF_REQUIRE(s && x_host && rowptr_host && col_host && ew_host && ticket, "null pointer");
     NERRF_REQUIRE(s->has_weights, "session has no weights (call nerrf_sage_session_set_weights)");
     NERRF_REQUIRE(n_nodes >= 0 && n_nodes <= s->max_nodes && n_edges >= 0 && n_edges <= s->max_edges,
                   "graph (%lld nodes, %lld edges) exceeds the session capacity", (long long)n_nodes, (long long)n_edges);
-    if (n_nodes == 0) return NERRF_OK;
-    cudaStream_t st = s->st, cst = s->cst;
+    const uint64_t t = ++s->next_ticket;
+    const int k = (int)(t % SESSION_SLOTS);
+    *ticket = t;
+    if (s->slot_ticket[k]) NERRF_CHECK_CUDA(cudaEventSynchronize(s->out_done[k]));   // at most SESSION_SLOTS steps in flight
+    s->slot_ticket[k] = t;
+    cudaStream_t st = s->st, cst = s->cst, dst = s->dst;
+    if (n_nodes == 0) {
+        NERRF_CHECK_CUDA(cudaEventRecord(s->compute_done[k], st));
+        NERRF_CHECK_CUDA(cudaEventRecord(s->out_done[k], st));
+        return NERRF_OK;
+    }
+    float *dx = s->x[k], *dew = s->ew[k], *dscore = s->score[k];
+    int32_t *drp = s->rowptr[k], *dcol = s->col[k];
     const size_t ws_bytes = session_ws_bytes(s->max_nodes, s->max_edges, s->hidden);
     int rc;
+    // the slot's inputs were last read by the compute of ticket t - SESSION_SLOTS (complete: out_done was waited above)
     if (s->L >= 2 && n_edges >= (1 << 20)) {
-        // Overlap: x and rowptr first, then col / ew in SESSION_CHUNKS edge-balanced, row-aligned chunks on
-        // the copy stream; layer 1 of a row range starts as soon as its edge chunk has landed.  Layers 2.. need the whole
-        // h_1 and therefore the whole upload, so what can hide is layer 1 (0.6 of the 2.65 ms of compute at cfg 2) under
-        // the edge arrays (80 of the 212 MB); the rest of the step is PCIe time + layers 2..L.
+        // Overlap inside a step: x and rowptr first, then col / ew in SESSION_CHUNKS edge-balanced,
+        // row-aligned chunks; layer 1 of a row range starts as soon as its edge chunk has landed.  Layers 2.. need the
+        // whole h_1 and therefore the whole upload.
         int64_t cut[SESSION_CHUNKS + 1];
         cut[0] = 0; cut[SESSION_CHUNKS] = n_nodes;
-        for (int k = 1; k < SESSION_CHUNKS; ++k) {                   // first row whose edge offset reaches k/C of the edges
-            const int64_t target = n_edges * k / SESSION_CHUNKS;
-            int64_t lo = cut[k - 1], hi = n_nodes;
+        for (int c = 1; c < SESSION_CHUNKS; ++c) {                   // first row whose edge offset reaches c/C of the edges
+            const int64_t target = n_edges * c / SESSION_CHUNKS;
+            int64_t lo = cut[c - 1], hi = n_nodes;
             while (lo < hi) { const int64_t mid = (lo + hi) / 2; if ((int64_t)rowptr_host[mid] < target) lo = mid + 1; else hi = mid; }
-            cut[k] = lo;
+            cut[c] = lo;
         }
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, cst));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, cst));
-        for (int k = 0; k < SESSION_CHUNKS; ++k) {
-            const int64_t e0 = rowptr_host[cut[k]], e1 = rowptr_host[cut[k + 1]];
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(drp, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(dx, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, cst));
+        for (int c = 0; c < SESSION_CHUNKS; ++c) {
+            const int64_t e0 = rowptr_host[cut[c]], e1 = rowptr_host[cut[c + 1]];
             if (e1 > e0) {
-                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col + e0, col_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
-                NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew + e0, ew_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
+                NERRF_CHECK_CUDA(cudaMemcpyAsync(dcol + e0, col_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
+                NERRF_CHECK_CUDA(cudaMemcpyAsync(dew + e0, ew_host + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cst));
             }
-            NERRF_CHECK_CUDA(cudaEventRecord(s->ev[k], cst));
+            NERRF_CHECK_CUDA(cudaEventRecord(s->ev[k][c], cst));
         }
         const size_t pp = (((size_t)n_nodes * s->hidden * sizeof(float) + 255) & ~(size_t)255);
         void* long_ws = ws_bytes > pp + 8192 ? (void*)((unsigned char*)s->ws + pp) : nullptr;
         const size_t long_ws_bytes = long_ws ? ws_bytes - pp : 0;
-        const float* in = s->x;
+        const float* in = dx;
         int F = s->f_in;
         for (int l = 0; l < s->L; ++l) {
             float* o = ((s->L - 1 - l) % 2 == 0) ? s->h : s->ws;
             const bool last = l == s->L - 1;
             if (l == 0) {
-                for (int k = 0; k < SESSION_CHUNKS; ++k) {
-                    NERRF_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev[k], 0));
-                    if (cut[k + 1] > cut[k]) {
-                        rc = layer_fwd_impl(in, s->rowptr, 0, s->col, s->ew, s->Wd[l], s->bd[l], o, n_nodes, cut[k], cut[k + 1], F, s->hidden, 1,
+                for (int c = 0; c < SESSION_CHUNKS; ++c) {
+                    NERRF_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev[k][c], 0));
+                    if (cut[c + 1] > cut[c]) {
+                        rc = layer_fwd_impl(in, drp, 0, dcol, dew, s->Wd[l], s->bd[l], o, n_nodes, cut[c], cut[c + 1], F, s->hidden, 1,
                                             algo & 0xFF, nullptr, 0.f, nullptr, long_ws, long_ws_bytes, nullptr, 0, nullptr, st);
                         if (rc) return rc;
                     }
                 }
             } else {
-                rc = layer_fwd_impl(in, s->rowptr, 0, s->col, s->ew, s->Wd[l], s->bd[l], o, n_nodes, 0, n_nodes, F, s->hidden, 1,
+                rc = layer_fwd_impl(in, drp, 0, dcol, dew, s->Wd[l], s->bd[l], o, n_nodes, 0, n_nodes, F, s->hidden, 1,
                                     (algo & 0xFF) | (l > 1 ? NERRF_SAGE_FLAG_REUSE_LONG_SCAN : 0), last ? s->node_w : nullptr, s->node_b,
-                                    last ? s->score : nullptr, long_ws, long_ws_bytes, nullptr, 0, nullptr, st);
+                                    last ? dscore : nullptr, long_ws, long_ws_bytes, nullptr, 0, nullptr, st);
                 if (rc) return rc;
             }
             in = o;
             F = s->hidden;
         }
     } else {
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->rowptr, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->col, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->ew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st));
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(s->x, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, st));
-        rc = nerrf_sage_forward(s->x, s->rowptr, 0, s->col, s->ew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
-                                s->node_w, s->node_b, s->h, s->score, s->ws, ws_bytes, algo, st);
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(drp, rowptr_host, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(dcol, col_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(dew, ew_host, (size_t)n_edges * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(dx, x_host, (size_t)n_nodes * s->f_in * 4, cudaMemcpyHostToDevice, cst));
+        NERRF_CHECK_CUDA(cudaEventRecord(s->ev[k][0], cst));
+        NERRF_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev[k][0], 0));
+        rc = nerrf_sage_forward(dx, drp, 0, dcol, dew, n_nodes, s->f_in, s->hidden, s->L, s->Wd, s->bd,
+                                s->node_w, s->node_b, s->h, dscore, s->ws, ws_bytes, algo, st);
         if (rc) return rc;
     }
-    if (score_out_host)
-        NERRF_CHECK_CUDA(cudaMemcpyAsync(score_out_host, s->score, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, st));
-    if (h_out_host)
+    if (h_out_host)     // the activations are shared by consecutive steps: their read-back stays on the compute stream
         NERRF_CHECK_CUDA(cudaMemcpyAsync(h_out_host, s->h, (size_t)n_nodes * s->hidden * 4, cudaMemcpyDeviceToHost, st));
-    NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
+    NERRF_CHECK_CUDA(cudaEventRecord(s->compute_done[k], st));
+    NERRF_CHECK_CUDA(cudaStreamWaitEvent(dst, s->compute_done[k], 0));
+    if (score_out_host)
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(score_out_host, dscore, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, dst));
+    NERRF_CHECK_CUDA(cudaEventRecord(s->out_done[k], dst));
     return NERRF_OK;
+}
+
+extern "C" int nerrf_sage_session_wait(nerrf_sage_session* s, uint64_t ticket) {
+    NERRF_REQUIRE(s, "null session");
+    NERRF_REQUIRE(ticket >= 1 && ticket <= s->next_ticket, "unknown ticket %llu", (unsigned long long)ticket);
+    const int k = (int)(ticket % SESSION_SLOTS);
+    if (s->slot_ticket[k] != ticket) return NERRF_OK;                // an older ticket: its slot was reused, i.e. it completed
+    NERRF_CHECK_CUDA(cudaEventSynchronize(s->out_done[k]));
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_sage_session_forward_host(nerrf_sage_session* s, const float* x_host, const int32_t* rowptr_host,
+                                               const int32_t* col_host, const float* ew_host, int64_t n_nodes,
+                                               int64_t n_edges, float* score_out_host, float* h_out_host, int algo) {
+    uint64_t t = 0;
+    int rc = nerrf_sage_session_submit_host(s, x_host, rowptr_host, col_host, ew_host, n_nodes, n_edges, score_out_host,
+                                            h_out_host, algo, &t);
+    if (rc) return rc;
+    return nerrf_sage_session_wait(s, t);
 }
 
 extern "C" int nerrf_sage_session_destroy(nerrf_sage_session* s) {
     if (!s) return NERRF_OK;
-    cudaFree(s->x); cudaFree(s->rowptr); cudaFree(s->col); cudaFree(s->ew); cudaFree(s->h); cudaFree(s->ws);
-    cudaFree(s->score); cudaFree(s->node_w);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->cst) cudaStreamSynchronize(s->cst);
+    if (s->dst) cudaStreamSynchronize(s->dst);
+    for (int k = 0; k < SESSION_SLOTS; ++k) {
+        cudaFree(s->x[k]); cudaFree(s->rowptr[k]); cudaFree(s->col[k]); cudaFree(s->ew[k]); cudaFree(s->score[k]);
+        for (int i = 0; i < SESSION_CHUNKS; ++i) if (s->ev[k][i]) cudaEventDestroy(s->ev[k][i]);
+        if (s->compute_done[k]) cudaEventDestroy(s->compute_done[k]);
+        if (s->out_done[k]) cudaEventDestroy(s->out_done[k]);
+    }
+    cudaFree(s->h); cudaFree(s->ws); cudaFree(s->node_w);
     for (int l = 0; l < 64; ++l) { if (s->Wd[l]) cudaFree(s->Wd[l]); if (s->bd[l]) cudaFree(s->bd[l]); }
     if (s->st) cudaStreamDestroy(s->st);
     if (s->cst) cudaStreamDestroy(s->cst);
-    for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->dst) cudaStreamDestroy(s->dst);
     delete s;
     return NERRF_OK;
 }

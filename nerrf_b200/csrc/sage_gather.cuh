@@ -16,7 +16,9 @@ namespace nerrf {
 // 2*UH load instructions (2*UH*G source rows) are issued BEFORE anything is consumed.  Weights are
 // re-broadcast at consume time instead of being held in registers.
 // wsum_out != nullptr: return the UNNORMALISED weighted sum and store the weight sum (used for chunk partials).
-template <int F, int UH = 0>
+// STRIDE: floats between consecutive source rows (F for a dense [n, F] matrix; the backward pass gathers the right half of
+// dZ [n, 2F] with STRIDE = 2F).
+template <int F, int UH = 0, int STRIDE = F>
 __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const int32_t* __restrict__ col,
                                               const float* __restrict__ ew, int64_t e0, int64_t e1, int lane,
                                               float* wsum_out = nullptr) {
@@ -43,7 +45,7 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ x, const 
             for (int u = 0; u < 2 * U; ++u) {
                 const int idx = j + u * G + g;
                 const int c = __shfl_sync(0xffffffffu, my_c, idx & 31);
-                v[u] = (idx < n) ? ldg4(xs + (int64_t)c * F) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u] = (idx < n) ? ldg4(xs + (int64_t)c * STRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 2 * U; ++u) {

@@ -121,6 +121,37 @@ def test_host_session_matches_device_path():
     sess.close()
 
 
+def test_host_session_pipelined_submit_wait():
+    """nerrf_sage_session_submit_host / _wait: a stream of DIFFERENT graphs, two in flight; every ticket's outputs equal
+    the device path's for its own graph (buffer sets never mix), in any wait order."""
+    model = GraphSAGE_T(32, 128, 3).cuda()
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    graphs = [G.synthetic_graph(N=20000 + 3000 * i, E=1100000 + 50000 * i if i % 2 else 90000, seed=30 + i) for i in range(5)]
+    want = [tuple(t.cpu() for t in model(*dev_graph(g))) for g in graphs]
+    sess = HostSession(model, 40000, 1400000)
+    host = [(pin(g.x), pin(g.rowptr), pin(g.col), pin(g.ew), torch.empty(g.num_nodes).pin_memory(),
+             torch.empty(g.num_nodes, 128).pin_memory() if i % 2 == 0 else None) for i, g in enumerate(graphs)]
+    tickets = []
+    for i, hb in enumerate(host):                      # depth-2 pipeline: submit i, then wait i-1
+        tickets.append(sess.submit(*hb))
+        if i >= 1:
+            sess.wait(tickets[i - 1])
+    sess.wait(tickets[-1])
+    sess.wait(tickets[0])                                # waiting an old ticket again is a no-op
+    for i, hb in enumerate(host):
+        assert torch.equal(hb[4], want[i][1]), f"scores of ticket {i}"
+        if hb[5] is not None:
+            assert torch.equal(hb[5], want[i][0]), f"embeddings of ticket {i}"
+    # three submits without a wait: the third blocks on the oldest internally, results still right
+    ts = [sess.submit(*host[i]) for i in (2, 3, 4)]
+    for t in ts:
+        sess.wait(t)
+    assert torch.equal(host[4][4], want[4][1]) and torch.equal(host[2][4], want[2][1])
+    with pytest.raises(L.NerrfError):
+        sess.wait(10 ** 6)
+    sess.close()
+
+
 def _ranking_matches(sc_gpu, sc_ref, k, err):
     """Top-k anomalous-node indices.  Exact equality is required for the prefix of the oracle's ranking whose adjacent
     score margins exceed 20x the measured max score error (there a flip would be a real bug); past the first
