@@ -5,10 +5,13 @@ gate "GNN / LSTM ROC-AUC >= 0.90 on the toy set" (ROADMAP.md:26,62-69); labels /
 docs/content/docs/threat-model.mdx:176-203,277-292.
 
 Training is NOT the north-star hot path (that is inference: GraphSAGE_T.forward, lstm.forward, mcts.search,
-rewards.score -- CUDA only).  It differentiates a plain-torch statement of the same frozen spec with autograd, on
-whatever device the parameters live on, and updates the very nn.Parameters the CUDA inference kernels read
-(GraphSAGE_T.weights / biases / node_w / node_b; LSTMScorer.lstm / head).  Inference never calls anything in this
-file, and nothing here is a fallback for it: GraphSAGE_T.forward / LSTMScorer.forward still refuse CPU tensors.
+rewards.score -- CUDA only).  With `--device cuda` the GraphSAGE-T half trains through the library's own kernels: the
+fused tcgen05 layer forward and the hand-written backward (`nerrf_sage_layer_bwd`, csrc/sage_bwd.cu) behind a
+torch.autograd.Function (nerrf_b200.ai.autograd); on the CPU it differentiates a plain-torch statement of the same frozen
+spec (also the thing the CUDA gradients are tested against).  The BiLSTM half is torch.nn.LSTM under autograd on either
+device.  Both update the very nn.Parameters the CUDA inference kernels read (GraphSAGE_T.weights / biases / node_w /
+node_b; LSTMScorer.lstm / head).  Inference never calls anything in this file, and nothing here is a fallback for it:
+GraphSAGE_T.forward / LSTMScorer.forward still refuse CPU tensors.
 
     python -m nerrf_b200.ai.train --traces 8 --epochs 200 --out weights.pt
 """
@@ -40,6 +43,18 @@ def sage_node_logits(model: GraphSAGE_T, x, rowptr, col, ew):
         agg = torch.zeros(N, h.shape[1], device=x.device, dtype=x.dtype).index_add_(0, dst, h[src] * ew[:, None])
         h = torch.relu(torch.cat([h, agg / wsum[:, None]], 1) @ W + b)
     return h @ model.node_w + model.node_b
+
+
+def node_logits(model: GraphSAGE_T, ex):
+    """Node-head logits of one example with gradients: on a CUDA device through the library's own kernels (fused tcgen05
+    forward + csrc/sage_bwd.cu backward, nerrf_b200.ai.autograd), on the CPU through the plain-torch restatement above."""
+    if ex["x"].is_cuda:
+        from . import autograd as AG
+        tg = ex.get("_train_graph")
+        if tg is None:
+            tg = ex["_train_graph"] = AG.TrainGraph(ex["rowptr"], ex["col"], ex["ew"])
+        return AG.sage_node_logits(model, ex["x"], tg)
+    return sage_node_logits(model, ex["x"], ex["rowptr"], ex["col"], ex["ew"])
 
 
 def lstm_logits(scorer: LSTMScorer, seq, lengths):
@@ -130,7 +145,7 @@ def train(model: GraphSAGE_T, scorer: LSTMScorer | None, examples, epochs: int =
         total = 0.0
         for ex in data:
             opt.zero_grad()
-            logit = sage_node_logits(model, ex["x"], ex["rowptr"], ex["col"], ex["ew"])
+            logit = node_logits(model, ex)
             m = ex["is_file"]
             pos = ex["label"][m].sum().clamp_min(1.0)
             loss = bce(logit[m], ex["label"][m], pos_weight=((m.sum() - pos) / pos).clamp(0.2, 5.0))

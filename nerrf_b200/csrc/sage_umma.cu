@@ -428,6 +428,14 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     // destinations: a 32-row tile can hold 50x the edges of an average one), a static round-robin left whole SMs idle.
     constexpr int TILE_RING = 16;                  // > IDX_STAGES + STAGES + 2 accumulators: an entry outlives its tile
     volatile int* tile_ids = reinterpret_cast<volatile int*>(smem_gen + (bar_base + 1024 - 64 - smem_base));
+    // QUAD mode (F = 32): a gather warp works on FOUR rows at a time, one per 8-lane group (a 128-byte source row is 8 lanes
+    // x 16 B), so the per-row overhead -- row setup, the cross-group combine, the bf16 split, the operand stores, the barrier
+    // arrivals -- is paid once per four rows and by all 32 lanes (r1/r2 ncu: the F=32 layer was issue-bound at ~500
+    // instructions per row, most of them this overhead).  Units of 4 rows are dealt round-robin to the warps; a warp need not
+    // own a unit in every tile, so the end of the tile stream is also published in `end_tl` (the closing tile's index).
+    constexpr bool QUAD = (F == 32) && !BULK;
+    volatile int* end_tl = reinterpret_cast<volatile int*>(smem_gen + (bar_base + 1024 - 64 - 8 - smem_base));
+    static_assert(256 + GATHER_WARPS * NQ * 8 <= 1024 - 64 - 8, "barrier area");
     unsigned char* idx_gen = smem_gen + (idx_base - smem_base);
     const uint32_t ring_base = bar_base + 1024;
     float* head_red = reinterpret_cast<float*>(smem_gen + (ring_base - smem_base) + (size_t)GATHER_WARPS * C::RING_BYTES);   // [2][4][32]
@@ -439,11 +447,12 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), TN); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), QUAD ? TN / 4 : TN); mbar_init(empty_bar(s), 1); }
+            *end_tl = 0x7fffffff;
             for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), EPI_WARPS * 32); }
             // idx full: ONE arrive.expect_tx by the loader (publishes the rowptr words, counts the bytes of the two bulk
             // copies); empty: one per gather warp.  ring slots: one arrive.expect_tx by the issuing lane per use
-            for (int q = 0; q < IDX_STAGES; ++q) { mbar_init(idxf_bar(q), 1); mbar_init(idxe_bar(q), GATHER_WARPS); }
+            for (int q = 0; q < IDX_STAGES; ++q) { mbar_init(idxf_bar(q), 1); mbar_init(idxe_bar(q), QUAD ? TN / 4 : GATHER_WARPS); }
             for (int g = 0; g < GATHER_WARPS; ++g)
                 for (int q = 0; q < NQ; ++q) mbar_init(ring_bar(g, q), 1);
             fence_barrier_init();
@@ -483,6 +492,225 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
     tc_fence_after();
 
     if (warp >= GATHER_WARP0) {
+      if constexpr (QUAD) {
+        // =========================================================== gather warps, QUAD mode (F = 32): see above
+        constexpr int UPT = TN / 4;                                       // units (4 rows) per tile
+        constexpr int SLOT_BYTES = 4 * 4 * F * 4;                         // a sub-batch = 4 steps x 4 rows x 128 B = 2 KB
+        static_assert(SLOT_BYTES * NQ == C::RING_BYTES, "ring layout");
+        const int g = warp - GATHER_WARP0;
+        const int grp = lane >> 3, sub = lane & 7;
+        // ring slot layout [step][group][8 lanes x 16 B] = lane-linear: conflict-free 16-byte shared loads
+        const uint32_t ring_u32 = ring_base + (uint32_t)(g * C::RING_BYTES) + (uint32_t)(lane * 16);
+        const float* ring_gen = reinterpret_cast<const float*>(smem_gen + (ring_base - smem_base) + (size_t)g * C::RING_BYTES) + lane * 4;
+        const float* xs = x + 4 * sub;
+        int stream_end = 0x7fffff00;                                      // in units
+
+        // per-unit state; e0 / items / row / long are per GROUP (each 8-lane group has its own row), nb is warp-uniform
+        int iu = g, ib = 0, inb = 1, ie0 = 0, iitems = 0, ilong = -1, itl = -1, itile = 0;  uint32_t irow = 0;  bool ifast = true;
+        const int32_t* icol = nullptr; int64_t ielo = 0;
+        int cu = g, cb = 0, cnb = 1, ce0 = 0, citems = 0, clong = -1, ctl = -1, ctile = 0;  bool cfast = true;
+        const float* cew = nullptr; int64_t celo = 0;
+
+        // Set up unit `iu` for issuing.  NEVER blocks: a warp runs up to NQ-1 sub-batches = up to 3 units = ~7 tiles ahead of
+        // what it has consumed, more than there are edge-block stages, so blocking here for a stage that is waiting for this
+        // very warp's consumption would deadlock.  false = the unit's tile is not staged yet (the caller emits an empty
+        // "bubble" group and retries at its next call) or the stream ended before it (stream_end shrinks to iu).
+        auto try_setup_issue_unit = [&]() -> bool {
+            const int tl = iu / UPT, r = (iu % UPT) * 4 + grp;
+            if (tl != itl) {
+                uint32_t done;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(idxf_bar(tl % IDX_STAGES)), "r"((uint32_t)(tl / IDX_STAGES) & 1u) : "memory");
+                if (!__all_sync(0xffffffffu, done != 0)) {               // every lane must have acquired the loader's writes
+                    if (__any_sync(0xffffffffu, *end_tl < tl)) stream_end = iu;    // the tile will never come
+                    return false;
+                }
+                itl = tl;
+                itile = tile_ids[tl % TILE_RING];
+                if (itile < 0) stream_end = (tl + 1) * UPT;              // the closing tile: its units carry the end of stream on
+            }
+            const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
+            icol = reinterpret_cast<const int32_t*>(ibp) + rp_s[96 + 2];
+            ielo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
+            const int64_t row = row_begin + (int64_t)itile * TN + r;
+            ib = 0; iitems = 0; ilong = -1; ifast = true;
+            if (itile >= 0 && row < row_end) {
+                irow = (uint32_t)row;
+                ie0 = rp_s[r];
+                const int deg = rp_s[r + 1] - ie0;
+                iitems = deg + 1;                                        // [self, edges...]
+                if (LONG && deg > LONG_T && lw.cap > 0) {
+                    ilong = long_lookup(lw, row);
+                    if (ilong >= 0) iitems = 1 + (deg + LONG_CH - 1) / LONG_CH;
+                }
+                ifast = ilong < 0 && ie0 + deg <= EMAX;
+            }
+            inb = __reduce_max_sync(0xffffffffu, (iitems + 3) >> 2);
+            inb = inb > 0 ? inb : 1;                                     // an all-invalid unit still travels as one empty sub-batch
+            ifast = __all_sync(0xffffffffu, ifast);
+            return true;
+        };
+        auto setup_consume_unit = [&]() {                                // cu < stream_end, tile already staged
+            const int tl = cu / UPT, r = (cu % UPT) * 4 + grp;
+            if (tl != ctl) ctile = tile_ids[tl % TILE_RING];
+            ctl = tl;
+            const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
+            const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
+            cew = reinterpret_cast<const float*>(ibp + EPAD * 4) + rp_s[96 + 3];
+            celo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
+            const int64_t row = row_begin + (int64_t)ctile * TN + r;
+            cb = 0; citems = 0; clong = -1; cfast = true;
+            if (ctile >= 0 && row < row_end) {
+                ce0 = rp_s[r];
+                const int deg = rp_s[r + 1] - ce0;
+                citems = deg + 1;
+                if (LONG && deg > LONG_T && lw.cap > 0) {
+                    clong = long_lookup(lw, row);
+                    if (clong >= 0) citems = 1 + (deg + LONG_CH - 1) / LONG_CH;
+                }
+                cfast = clong < 0 && ce0 + deg <= EMAX;
+            }
+            cnb = __reduce_max_sync(0xffffffffu, (citems + 3) >> 2);
+            cnb = cnb > 0 ? cnb : 1;
+            cfast = __all_sync(0xffffffffu, cfast);
+        };
+        // one cp.async group = sub-batch `ib` of the issue unit: 4 steps, step s = item ib*4+s of each of the 4 rows
+        bool iready = false, cready = false;
+        uint32_t bubbles = 0;                                             // bit q: nothing was issued into ring slot q
+        auto issue = [&](int slot) {
+            if (iu < stream_end && !iready) iready = try_setup_issue_unit();       // may shrink stream_end
+            bubbles |= 1u << slot;
+            if (iu < stream_end && iready) {
+                bubbles &= ~(1u << slot);
+                const int first = ib * 4;
+                const uint32_t dst = ring_u32 + (uint32_t)(slot * SLOT_BYTES);
+                if (ifast) {                                             // every row of the unit staged in full: branch free
+                    uint32_t src[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) src[st] = (uint32_t)icol[ie0 + first + st - 1];   // slack reads stay in smem
+                    if (first == 0) src[0] = irow;                       // item 0 of every row is its self row
+#pragma unroll
+                    for (int st = 0; st < 4; ++st)
+                        cp_async16_pred(dst + (uint32_t)(st * 512), xs + (size_t)src[st] * F, first + st < iitems);
+                } else {
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        const int it = first + st;
+                        if (it < iitems) {
+                            const float* srcp;
+                            if (it == 0) srcp = xs + (size_t)irow * F;
+                            else if (LONG && ilong >= 0) srcp = lw.partial + (size_t)(ilong + it - 1) * 128 + 4 * sub;
+                            else {
+                                const int k = ie0 + it - 1;
+                                srcp = xs + (size_t)(uint32_t)((k < EMAX) ? icol[k] : __ldg(col + ielo + k)) * F;
+                            }
+                            cp_async16(dst + (uint32_t)(st * 512), srcp);
+                        }
+                    }
+                }
+                if (++ib >= inb) { iu += GATHER_WARPS; iready = false; }
+            }
+            cp_async_commit();                                            // (possibly empty) group keeps the count in step
+        };
+
+        int islot = 0, cslot = 0;
+#pragma unroll
+        for (int d = 0; d < NQ - 1; ++d) { issue(islot); islot = (islot + 1) % NQ; }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), self = acc;
+        float wsum = 0.f;
+        int last_tl = -1;
+        while (cu < stream_end) {
+            cp_async_wait<NQ - 2>();
+            __syncwarp();
+            issue(islot);
+            islot = (islot + 1) % NQ;
+            if ((bubbles >> cslot) & 1u) {                                // a bubble: the unit's tile was not staged yet
+                cslot = (cslot + 1) % NQ;
+                __nanosleep(64);
+                continue;
+            }
+            if (!cready) { setup_consume_unit(); cready = true; }         // first sub-batch of the unit (its tile is staged: the
+                                                                          // issue side saw it, and this warp has not released it)
+            {
+                const int first = cb * 4;
+                const float* rs = ring_gen + cslot * (SLOT_BYTES / 4);
+                if (cfast) {
+                    float4 v[4];
+                    float w[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        v[st] = *reinterpret_cast<const float4*>(rs + st * 128);
+                        w[st] = cew[ce0 + first + st - 1];
+                    }
+                    if (first == 0) { self = v[0]; w[0] = 0.f; v[0] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        if (first + st < citems) {
+                            wsum += w[st];
+                            acc.x = fmaf(w[st], v[st].x, acc.x); acc.y = fmaf(w[st], v[st].y, acc.y);
+                            acc.z = fmaf(w[st], v[st].z, acc.z); acc.w = fmaf(w[st], v[st].w, acc.w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        const int it = first + st;
+                        if (it < citems) {
+                            const float4 v = *reinterpret_cast<const float4*>(rs + st * 128);
+                            if (it == 0) {
+                                self = v;
+                            } else if (LONG && clong >= 0) {             // chunk partial: already weighted
+                                wsum += lw.pw[clong + it - 1];
+                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                            } else {
+                                const int k = ce0 + it - 1;
+                                const float w = (k < EMAX) ? cew[k] : __ldg(ew + celo + k);
+                                wsum += w;
+                                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                            }
+                        }
+                    }
+                }
+            }
+            cslot = (cslot + 1) % NQ;
+            if (++cb < cnb) continue;
+
+            // ---- unit complete: all 32 lanes normalise, split and store their 4 columns of their group's row
+            const int tl = ctl;
+            const int r = (cu % UPT) * 4 + grp;
+            const int s = tl % C::STAGES;
+            if (tl != last_tl) {
+                mbar_wait(empty_bar(s), ((uint32_t)(tl / C::STAGES) & 1u) ^ 1u);
+                last_tl = tl;
+            }
+            if (citems > 0) {
+                const float inv = 1.0f / fmaxf(wsum, 1e-12f);
+                const float4 mean = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+                unsigned char* st = smem_gen + (size_t)s * C::STAGE_BYTES;
+                uint2 parts[NS];
+                split4<NS>(self, parts);
+                uint32_t off = b_offset(r, 4 * sub);
+#pragma unroll
+                for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+                split4<NS>(mean, parts);
+                off = b_offset(r, F + 4 * sub);
+#pragma unroll
+                for (int p = 0; p < NS; ++p) *reinterpret_cast<uint2*>(st + p * C::PART_BYTES + off) = parts[p];
+            }
+            fence_proxy_async();
+            acc = make_float4(0.f, 0.f, 0.f, 0.f); self = acc; wsum = 0.f;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(full_bar(s));
+                mbar_arrive(idxe_bar(tl % IDX_STAGES));                  // one arrival per unit (the stage has UPT of them)
+            }
+            cu += GATHER_WARPS;
+            cready = false;
+        }
+        cp_async_wait<0>();
+      } else {
         // =========================================================== gather warps (producers of the B operand)
         // Row stream of this warp: i = g, g+G, g+2G, ... over the CTA's tiles.  A row is the item list
         // [self, edge_0 .. edge_{deg-1}], cut into sub-batches of QS items.  Every item is ONE bulk async copy of a
@@ -752,6 +980,7 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             if (ci < stream_end) setup_consume_row();
         }
         if constexpr (!BULK) cp_async_wait<0>();
+      }
     } else if (warp == LOADER_WARP) {
         // =========================================================== edge-block loader
         constexpr int RPW = (TN + 1 + 31) / 32;
@@ -764,36 +993,40 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                 rp[k] = (lane + 32 * k <= TN) ? (int64_t)rowptr[rr] : 0;
             }
         };
-        int64_t rp[RPW], rp_next[RPW];
-        auto claim = [&]() -> int64_t {                                  // next unclaimed tile of the launch (or >= n_tiles)
-            unsigned v = 0;
-            if (lane == 0) v = atomicAdd(tile_ctr, 1u);
-            return (int64_t)__shfl_sync(0xffffffffu, v, 0);
-        };
-        int64_t tile = claim();
-        if (tile < n_tiles) load_rp(tile, rp);
-        for (int64_t tl = 0;; ++tl) {
+        // Software pipeline, two tiles deep and free of register copies (the loop body is instantiated twice with the roles of
+        // the two rowptr register sets swapped): the atomic that claims tile t+2 and the rowptr loads of tile t+1 are issued
+        // in iteration t and first needed one iteration later, so neither latency (~1 us each) sits on the per-tile path --
+        // at F=32 a tile period is < 2 us and the r1/r2 loader (claim -> dependent loads -> use, serial) was as slow as that.
+        unsigned craw = 0;                                               // lane 0: raw result of the claim in flight
+        auto claim_issue = [&]() { if (lane == 0) craw = atomicAdd(tile_ctr, 1u); };
+        auto claim_take = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, craw, 0); };
+        // one iteration: stage tile `tile` (its rowptr words in rp_cur) as the CTA's tl-th tile; returns true at the end of stream
+        auto body = [&](int64_t tl, int64_t tile, int64_t (&rp_cur)[RPW], int64_t& tile_nx, int64_t (&rp_nx)[RPW]) -> bool {
             const bool end = tile >= n_tiles;
-            int64_t next = n_tiles;
+            tile_nx = n_tiles;
             if (!end) {
-                next = claim();                                          // one tile ahead: its rowptr words are in flight
-                if (next < n_tiles) load_rp(next, rp_next);              // while we wait for a free stage
+                tile_nx = claim_take();                                  // claimed one iteration ago
+                claim_issue();                                           // for the iteration after the next
+                if (tile_nx < n_tiles) load_rp(tile_nx, rp_nx);          // needed in the next iteration
             }
             const int q = (int)(tl % IDX_STAGES);
             mbar_wait_relaxed(idxe_bar(q), ((uint32_t)(tl / IDX_STAGES) & 1u) ^ 1u);
-            if (lane == 0) tile_ids[tl % TILE_RING] = end ? -1 : (int)tile;
+            if (lane == 0) {
+                tile_ids[tl % TILE_RING] = end ? -1 : (int)tile;
+                if (end) *end_tl = (int)tl;                              // ordered before the closing release below
+            }
             if (end) {                                                   // closing entry: no rows, no edges
                 __syncwarp();
                 if (lane == 0) mbar_arrive_expect_tx(idxf_bar(q), 0u);
-                break;
+                return true;
             }
-            const int64_t e_lo = __shfl_sync(0xffffffffu, rp[0], 0);
-            const int64_t e_hi = __shfl_sync(0xffffffffu, rp[TN / 32], TN % 32);
+            const int64_t e_lo = __shfl_sync(0xffffffffu, rp_cur[0], 0);
+            const int64_t e_hi = __shfl_sync(0xffffffffu, rp_cur[TN / 32], TN % 32);
             unsigned char* ib = idx_gen + (size_t)q * IDX_STAGE_BYTES;
             int32_t* rp_s = reinterpret_cast<int32_t*>(ib + EPAD * 8);
 #pragma unroll
             for (int k = 0; k < RPW; ++k)
-                if (lane + 32 * k <= TN) rp_s[lane + 32 * k] = (int32_t)(rp[k] - e_lo);
+                if (lane + 32 * k <= TN) rp_s[lane + 32 * k] = (int32_t)(rp_cur[k] - e_lo);
             const int n = (int)((e_hi - e_lo) < EMAX ? (e_hi - e_lo) : EMAX);
             // the col / ew slices [e_lo, e_lo + n) as the 16-byte aligned supersets bulk copies need: the slice starts
             // `off` elements into its staged array (the gather warps add it); an over-read stays inside the 16-byte
@@ -815,9 +1048,16 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
                     bulk_g2s(ws, reinterpret_cast<const void*>(wa & ~(uintptr_t)15), w_bytes, idxf_bar(q));
                 }
             }
-#pragma unroll
-            for (int k = 0; k < RPW; ++k) rp[k] = rp_next[k];
-            tile = next;
+            return false;
+        };
+        int64_t rp_a[RPW], rp_b[RPW];
+        claim_issue();
+        int64_t tile_a = claim_take(), tile_b = n_tiles;
+        claim_issue();                                                   // in flight for the first body()
+        if (tile_a < n_tiles) load_rp(tile_a, rp_a);
+        for (int64_t tl = 0;; tl += 2) {
+            if (body(tl, tile_a, rp_a, tile_b, rp_b)) break;
+            if (body(tl + 1, tile_b, rp_b, tile_a, rp_a)) break;
         }
     } else if (warp == MMA_WARP) {
         // =========================================================== MMA issuer (one thread)
