@@ -58,7 +58,10 @@ template <int F, int NS>
 struct UmmaCfg {
     static constexpr int GATHER_WARPS = (F == 32) ? 18 : 14;  // F=32 leaves room for more rings (and needs more TLP)
     static constexpr int THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;
-    static constexpr int IDX_STAGES = (F == 32) ? 4 : 3;
+    // F = 32 (quad-mode gather): a warp runs up to 3 units = ~7 tiles ahead of what it has consumed and holds a tile's edge
+    // block from issue to completion, so the look-ahead is bounded by the number of edge-block stages, not by the rings
+    // (ncu r2g: with 4 stages 77 % of the issue-side polls found the next tile not staged)
+    static constexpr int IDX_STAGES = (F == 32) ? 9 : 3;
     static constexpr int K = 2 * F;
     static constexpr int KB = K / 64;                        // 128-byte K blocks
     static constexpr int KSTEPS = K / 16;                    // MMAs (K=16) per product
@@ -66,7 +69,7 @@ struct UmmaCfg {
     static constexpr int STAGE_BYTES = NS * PART_BYTES;
     static constexpr int QS = qs_for<F>();                    // 4 (F=128), 8 (F=64), 16 (F=32): always 2 KB per sub-batch
     static constexpr int RING_BYTES = NQ * QS * F * 4;       // per gather warp: NQ sub-batches x QS source rows
-    static constexpr int STAGES = (F == 128) ? 2 : 4;
+    static constexpr int STAGES = (F == 128) ? 2 : (F == 32 ? 3 : 4);
     static constexpr int W_PART_COLS = K / 2;                // W^T term p lives in TMEM columns [p*K/2, (p+1)*K/2)
     static constexpr int ACC_COL0 = NS * W_PART_COLS;
     static constexpr int TMEM_COLS = (ACC_COL0 + 2 * TN <= 256) ? 256 : 512;
@@ -519,7 +522,9 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             const int tl = iu / UPT, r = (iu % UPT) * 4 + grp;
             if (tl != itl) {
                 uint32_t done;
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                // test_wait, not try_wait: the latter may suspend the warp for a hardware time limit, and this poll sits in front of
+                // the consumption of data that has already landed
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(done) : "r"(idxf_bar(tl % IDX_STAGES)), "r"((uint32_t)(tl / IDX_STAGES) & 1u) : "memory");
                 if (!__all_sync(0xffffffffu, done != 0)) {               // every lane must have acquired the loader's writes
                     if (__any_sync(0xffffffffu, *end_tl < tl)) stream_end = iu;    // the tile will never come
@@ -531,10 +536,12 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             }
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
             const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
-            icol = reinterpret_cast<const int32_t*>(ibp) + rp_s[96 + 2];
+            // (the closing tile's stage holds no rowptr words: its slack reads must not follow a stale offset)
+            icol = reinterpret_cast<const int32_t*>(ibp) + (itile >= 0 ? rp_s[96 + 2] : 0);
             ielo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
             const int64_t row = row_begin + (int64_t)itile * TN + r;
             ib = 0; iitems = 0; ilong = -1; ifast = true;
+            if (itile < 0) ie0 = 1;
             if (itile >= 0 && row < row_end) {
                 irow = (uint32_t)row;
                 ie0 = rp_s[r];
@@ -557,10 +564,11 @@ sage_layer_umma_kernel(const float* __restrict__ x, const RP* __restrict__ rowpt
             ctl = tl;
             const unsigned char* ibp = idx_gen + (size_t)(tl % IDX_STAGES) * IDX_STAGE_BYTES;
             const int32_t* rp_s = reinterpret_cast<const int32_t*>(ibp + EPAD * 8);
-            cew = reinterpret_cast<const float*>(ibp + EPAD * 4) + rp_s[96 + 3];
+            cew = reinterpret_cast<const float*>(ibp + EPAD * 4) + (ctile >= 0 ? rp_s[96 + 3] : 0);
             celo = *reinterpret_cast<const int64_t*>(ibp + EPAD * 8 + 384);
             const int64_t row = row_begin + (int64_t)ctile * TN + r;
             cb = 0; citems = 0; clong = -1; cfast = true;
+            if (ctile < 0) ce0 = 1;
             if (ctile >= 0 && row < row_end) {
                 ce0 = rp_s[r];
                 const int deg = rp_s[r + 1] - ce0;
