@@ -44,23 +44,32 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Stage u / v / vw / cost (+ guard index) into smem, transposed: action a = lane*chunk + i lives at [i*32 + lane].
-struct TermsS { float *u, *v, *vw, *c; uint8_t* g; };
+// Staged reward terms, transposed (action a = lane*chunk + i lives at [i*32 + lane]): three tables of (data-loss term,
+// downtime term) PAIRS -- tab[0] = (u, 0) for an action that is NOT applied, tab[1] = (v, cost) applied, tab[2] = (vw, cost)
+// applied while its guard (kill) action is not -- so evaluating one action is one 8-byte shared load from the table the
+// state selects, + two rounded adds (r1/r2: five loads and three selects per action, ~600 instructions per state).
+struct TermsS { float2* tab; uint8_t* g; bool has_guard; };
 template <int NW>
 __device__ __forceinline__ TermsS carve_terms(unsigned char* smem) {
     constexpr int A_PAD = 1024 * NW;
     TermsS t;
-    t.u = reinterpret_cast<float*>(smem); t.v = t.u + A_PAD; t.vw = t.v + A_PAD; t.c = t.vw + A_PAD;
-    t.g = reinterpret_cast<uint8_t*>(t.c + A_PAD);
+    t.tab = reinterpret_cast<float2*>(smem);
+    t.g = reinterpret_cast<uint8_t*>(t.tab + 3 * A_PAD);
+    t.has_guard = false;
     return t;
 }
 template <int NW>
-constexpr size_t terms_smem_bytes() { return (size_t)1024 * NW * (4 * 4 + 1); }
+constexpr size_t terms_smem_bytes() { return (size_t)1024 * NW * (3 * 8 + 1); }
+// the search kernel appends one scratch bitset (32*NW words) per warp: the rank-space rollouts scatter their picks into it
+template <int NW>
+constexpr size_t mcts_smem_bytes() { return terms_smem_bytes<NW>() + (size_t)(896 / 32) * 32 * NW * 4; }
 
+// block-wide (contains a __syncthreads): fills the tables and reports whether any action has a guard
 template <int NW>
 __device__ __forceinline__ void stage_terms(const float* __restrict__ p, const float* __restrict__ size,
-                                            const float* __restrict__ cost, const int32_t* __restrict__ guard, int A, TermsS t) {
+                                            const float* __restrict__ cost, const int32_t* __restrict__ guard, int A, TermsS& t) {
     constexpr int CHUNK = 32 * NW, A_PAD = 1024 * NW;
+    int any = 0;
     for (int a = threadIdx.x; a < A_PAD; a += blockDim.x) {
         float u = 0.f, v = 0.f, vw = 0.f, c = 0.f;
         int g = 255;
@@ -71,29 +80,48 @@ __device__ __forceinline__ void stage_terms(const float* __restrict__ p, const f
             c = cost[a];
             vw = v;
             const int gd = guard ? guard[a] : -1;
-            if (gd >= 0 && gd < 32 && gd < A) { g = gd; vw = __fadd_rn(v, __fmul_rn(p[gd], u)); }
+            if (gd >= 0 && gd < 32 && gd < A) { g = gd; vw = __fadd_rn(v, __fmul_rn(p[gd], u)); any = 1; }
         }
         const int lane = a / CHUNK, i = a % CHUNK;
-        t.u[i * 32 + lane] = u; t.v[i * 32 + lane] = v; t.vw[i * 32 + lane] = vw; t.c[i * 32 + lane] = c;
+        t.tab[i * 32 + lane] = make_float2(u, 0.f);
+        t.tab[A_PAD + i * 32 + lane] = make_float2(v, c);
+        t.tab[2 * A_PAD + i * 32 + lane] = make_float2(vw, c);
         t.g[i * 32 + lane] = (uint8_t)g;
     }
+    t.has_guard = __syncthreads_or(any) != 0;
 }
 
 // score of the state held across a warp (lane holds words w[0..NW)), spec'd order.  All lanes return it.
 template <int NW>
 __device__ __forceinline__ float warp_score(const uint32_t (&w)[NW], const TermsS t, int lane) {
-    const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], 0);          // state word 0 holds the guard (kill) actions
+    constexpr int A_PAD = 1024 * NW;
     float dl = 0.f, dt = 0.f;
+    const float2* tab = t.tab + lane;
+    if (!t.has_guard) {                                                   // (uniform) no guards: two tables
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
+        for (int k = 0; k < NW; ++k) {
 #pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-            const int i = k * 32 + b;
-            const bool ap = (w[k] >> b) & 1u;
-            const unsigned gd = t.g[i * 32 + lane];
-            const bool guard_alive = gd < 32u && !((w0 >> gd) & 1u);
-            dl = __fadd_rn(dl, ap ? (guard_alive ? t.vw[i * 32 + lane] : t.v[i * 32 + lane]) : t.u[i * 32 + lane]);
-            dt = __fadd_rn(dt, ap ? t.c[i * 32 + lane] : 0.f);
+            for (int b = 0; b < 32; ++b) {
+                const int i = k * 32 + b;
+                const float2 e = tab[((w[k] >> b) & 1u) * A_PAD + i * 32];
+                dl = __fadd_rn(dl, e.x);
+                dt = __fadd_rn(dt, e.y);
+            }
+        }
+    } else {
+        const uint32_t w0 = __shfl_sync(0xffffffffu, w[0], 0);          // state word 0 holds the guard (kill) actions
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const int i = k * 32 + b;
+                const unsigned ap = (w[k] >> b) & 1u;
+                const unsigned gd = t.g[i * 32 + lane];
+                const unsigned guard_alive = (gd < 32u && !((w0 >> (gd & 31u)) & 1u)) ? 1u : 0u;
+                const float2 e = tab[(ap + (ap & guard_alive)) * A_PAD + i * 32];
+                dl = __fadd_rn(dl, e.x);
+                dt = __fadd_rn(dt, e.y);
+            }
         }
     }
 #pragma unroll
@@ -147,6 +175,21 @@ __device__ __forceinline__ void lane_zero_scan(const uint32_t (&w)[NW], int lane
         if (lane >= o) incl += t;
     }
     total = __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// position of the n-th (0-based) set bit of m (which has more than n set bits): 5 popc steps, branch free
+// (__fns compiles to a much longer sequence)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(m & ((1u << w) - 1u));
+        const bool up = n >= c;
+        pos += up ? w : 0;
+        n -= up ? c : 0;
+        m = up ? (m >> w) : m;
+    }
+    return pos;
 }
 
 // q-th zero bit of a state stored as a plain word array (single thread).
@@ -203,7 +246,8 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
     constexpr int A_PAD = 1024 * NW, NWORDS = 32 * NW;
     unsigned bar_target = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TermsS terms = carve_terms<NW>(smem_raw);
+    TermsS terms = carve_terms<NW>(smem_raw);
+    uint32_t* const s_scratch = reinterpret_cast<uint32_t*>(smem_raw + terms_smem_bytes<NW>()) + (threadIdx.x >> 5) * NWORDS;
     __shared__ uint32_t s_state[NWORDS];
     __shared__ int2 s_path[MAXD];
     __shared__ float s_key[MCTS_WARPS];
@@ -263,18 +307,27 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
             float best_key = -INFINITY;
             int best_a = 0x7fffffff;
             const size_t base = (size_t)node * A_PAD;
-            for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
-                if ((s_state[a >> 5] >> (a & 31)) & 1u) continue;
-                const int n = child_n[base + a];
-                float key;
-                if (n == 0) {
-                    key = INFINITY;
-                } else {
-                    const float nf = (float)n;
-                    const float q = __fdiv_rn(child_w[base + a], nf);
-                    key = __fadd_rn(q, __fmul_rn(P.c, __fsqrt_rn(__fdiv_rn(lnN, nf))));
+            for (int a0 = tid; a0 < A_PAD; a0 += 2 * MCTS_THREADS) {     // two actions per pass: their loads travel together
+                const int a1 = a0 + MCTS_THREADS;
+                const bool ok0 = !((s_state[a0 >> 5] >> (a0 & 31)) & 1u);
+                const bool ok1 = a1 < A_PAD && !((s_state[(a1 & (A_PAD - 1)) >> 5] >> (a1 & 31)) & 1u);
+                const int n0 = ok0 ? child_n[base + a0] : 0, n1 = ok1 ? child_n[base + a1] : 0;
+                const float cw0 = ok0 ? child_w[base + a0] : 0.f, cw1 = ok1 ? child_w[base + a1] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {                             // ascending a: strict > keeps the lowest
+                    const bool ok = u ? ok1 : ok0;
+                    const int n = u ? n1 : n0, a = u ? a1 : a0;
+                    if (!ok) continue;
+                    float key;
+                    if (n == 0) {
+                        key = INFINITY;
+                    } else {
+                        const float nf = (float)n;
+                        const float q = __fdiv_rn(u ? cw1 : cw0, nf);
+                        key = __fadd_rn(q, __fmul_rn(P.c, __fsqrt_rn(__fdiv_rn(lnN, nf))));
+                    }
+                    if (key > best_key) { best_key = key; best_a = a; }
                 }
-                if (key > best_key) { best_key = key; best_a = a; }     // ascending a: strict > keeps the lowest
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -331,7 +384,76 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
         // (8 lanes per rollout / 4 rollouts per warp was tried: the per-step chain of dependent collectives got LONGER --
         // the n-th-set-bit search has to run inside one lane -- and with 7 instead of 28 warps per SM nothing hid it:
         // 54 k instead of 30 k cycles for the phase, profiles/r02_mcts.md)
-        for (int r = (int)blockIdx.x * MCTS_WARPS + warp; r < P.R; r += (int)gridDim.x * MCTS_WARPS) {
+        // RANK-SPACE rollouts (round 2): a rollout applies "the j_k-th still-legal action" left times.  Instead of updating
+        // the warp-distributed bitset at every step (ballot -> ffs -> 2 shfl -> popc -> ballot -> ffs: a chain of dependent
+        // collectives, ~35 instructions), the picks are kept as a SORTED list of ranks among the leaf's legal actions, one
+        // slot per lane (two registers: 64 slots): with s_0 < s_1 < ... the earlier picks and t_i = s_i - i (non-decreasing),
+        // the j-th still-legal action has leaf rank j + c, c = #{i : t_i <= j} -- ONE ballot + popc -- and is inserted at
+        // slot c (one shfl_up; the shifted entries lose 1).  The ranks become bit positions once, at the end (each lane
+        // resolves its own picks: binary search over the per-word prefix counts + fns), scattered into a per-warp scratch
+        // bitset.  Same draws, same set, hence the same state and -- same summation order -- the same reward, bit for bit.
+        const bool rank_path = (P.D - depth) <= 64;
+        for (int r = (int)blockIdx.x * MCTS_WARPS + warp; rank_path && r < P.R; r += (int)gridDim.x * MCTS_WARPS) {
+            int left = P.D - depth;
+            int L = L0, n = 0;
+            int t_lo = 0x7fffffff, t_hi = 0x7fffffff;                    // slot lane / lane + 32; empty = +inf
+            auto pick = [&](int j) {
+                if (n < 32) {                                             // (uniform) the upper half is still empty
+                    const int c = __popc(__ballot_sync(0xffffffffu, t_lo <= j));
+                    const int up = __shfl_up_sync(0xffffffffu, t_lo, 1);
+                    t_lo = (lane < c) ? t_lo : (lane == c ? j : up - 1);
+                } else {
+                    const int c = __popc(__ballot_sync(0xffffffffu, t_lo <= j)) + __popc(__ballot_sync(0xffffffffu, t_hi <= j));
+                    const int up_lo = __shfl_up_sync(0xffffffffu, t_lo, 1);
+                    int up_hi = __shfl_up_sync(0xffffffffu, t_hi, 1);
+                    const int carry = __shfl_sync(0xffffffffu, t_lo, 31);
+                    if (lane == 0) up_hi = carry;
+                    t_lo = (lane < c) ? t_lo : (lane == c ? j : up_lo - 1);
+                    t_hi = (lane + 32 < c) ? t_hi : (lane + 32 == c ? j : up_hi - 1);
+                }
+                ++n;
+            };
+            if (first_move) { pick(r % L0); L -= 1; left -= 1; }
+            // every Philox block of the rollout at once: lane i computes block i (counter (r, i, t, 0)) -- at most 16 blocks
+            // for <= 64 steps -- instead of all 32 lanes computing the same block 13 times over (~100 instructions each)
+            uint32_t rnd[4];
+            philox4x32_10((uint32_t)r, (uint32_t)lane, (uint32_t)t, 0u, P.k0, P.k1, rnd);
+            const int nsteps = left < L ? left : L;                      // a step removes one legal action: min(left, L) steps
+            for (int k = 0; k < nsteps; k += 4) {                         // one Philox block feeds four steps
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t x = __shfl_sync(0xffffffffu, rnd[q], k >> 2);
+                    if (k + q < nsteps) pick((int)__umulhi(x, (uint32_t)(L - (k + q))));
+                }
+            }
+            // ranks -> bits: scratch = leaf state, then every pick sets its bit
+#pragma unroll
+            for (int k = 0; k < NW; ++k) s_scratch[lane * NW + k] = s_state[lane * NW + k];
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int slot = lane + 32 * half;
+                if (slot < n) {
+                    const int q = (half ? t_hi : t_lo) + slot;           // rank among the leaf's legal actions
+                    int lo_w = 0, hi_w = NWORDS - 1;                     // last word whose prefix count is <= q
+                    while (lo_w < hi_w) {
+                        const int mid = (lo_w + hi_w + 1) >> 1;
+                        if (s_pref[mid] <= q) lo_w = mid; else hi_w = mid - 1;
+                    }
+                    const int bit = nth_set_bit(~s_state[lo_w], q - s_pref[lo_w]);
+                    atomicOr(&s_scratch[lo_w], 1u << bit);
+                }
+            }
+            __syncwarp();
+            uint32_t w[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = s_scratch[lane * NW + k];
+            __syncwarp();                                                 // the scratch is reused by this warp's next rollout
+            const float sc = warp_score<NW>(w, terms, lane);
+            if (lane == 0) val[r] = __fmul_rn(__fsub_rn(sc, P.lo), P.inv_range);
+        }
+        // deeper rollouts (more than 64 steps below the leaf): the per-step bitset update
+        for (int r = (int)blockIdx.x * MCTS_WARPS + warp; !rank_path && r < P.R; r += (int)gridDim.x * MCTS_WARPS) {
             uint32_t w[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) w[k] = s_state[lane * NW + k];
@@ -372,22 +494,47 @@ __global__ void __launch_bounds__(MCTS_THREADS) mcts_search_kernel(MctsArgs P) {
         if (first_move) {   // leaf children: action a has rank q among the leaf's legal actions; fixed ascending-r accumulation
             const int nq = P.R < L0 ? P.R : L0;
             const size_t lbase = (size_t)leaf * A_PAD;
-            for (int a = tid; a < A_PAD; a += MCTS_THREADS) {
-                const uint32_t wv = s_state[a >> 5];
-                if ((wv >> (a & 31)) & 1u) continue;                     // not legal at the leaf
-                const int q = __popc(~wv & ((1u << (a & 31)) - 1u)) + s_pref[a >> 5];   // legal actions below a
-                if (q >= nq) continue;
-                float wsum = child_w[lbase + a];
-                int cnt = 0;
-                int r = q;
-                for (; r + 3 * L0 < P.R; r += 4 * L0) {                  // four loads in flight, added in ascending r
-                    const float v0 = __ldcg(val + r), v1 = __ldcg(val + r + L0), v2 = __ldcg(val + r + 2 * L0), v3 = __ldcg(val + r + 3 * L0);
-                    wsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(wsum, v0), v1), v2), v3);
-                    cnt += 4;
+            // the leaf was created THIS iteration or is terminal-by-depth: in both cases its child row is read here for the
+            // first time in this iteration, and a new leaf's row is still all zero -- so the row's old values are only loaded
+            // when the leaf already existed
+            const bool fresh = s_created != 0;
+            for (int a0 = tid; a0 < A_PAD; a0 += 2 * MCTS_THREADS) {     // two actions per pass: one latency round for both
+                int aa[2], qq[2];
+                bool on[2];
+                float wsum[2];
+                int cnt[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int a = a0 + u * MCTS_THREADS;
+                    aa[u] = a;
+                    const uint32_t wv = s_state[(a & (A_PAD - 1)) >> 5];
+                    qq[u] = __popc(~wv & ((1u << (a & 31)) - 1u)) + s_pref[(a & (A_PAD - 1)) >> 5];   // legal actions below a
+                    on[u] = a < A_PAD && !((wv >> (a & 31)) & 1u) && qq[u] < nq;                      // legal at the leaf, has rollouts
+                    wsum[u] = (on[u] && !fresh) ? child_w[lbase + a] : 0.f;
+                    cnt[u] = (on[u] && !fresh) ? child_n[lbase + a] : 0;
                 }
-                for (; r < P.R; r += L0) { wsum = __fadd_rn(wsum, __ldcg(val + r)); ++cnt; }
-                child_w[lbase + a] = wsum;
-                child_n[lbase + a] = child_n[lbase + a] + cnt;
+                float v[2][4];
+                int r[2] = {qq[0], qq[1]};
+                bool more = true;
+                while (more) {                                            // four loads per action in flight, added in ascending r
+                    more = false;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (on[u] && r[u] + i * L0 < P.R) v[u][i] = __ldcg(val + r[u] + i * L0);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (on[u] && r[u] + i * L0 < P.R) { wsum[u] = __fadd_rn(wsum[u], v[u][i]); ++cnt[u]; }
+                        r[u] += 4 * L0;
+                        more = more || (on[u] && r[u] < P.R);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (on[u]) { child_w[lbase + aa[u]] = wsum[u]; child_n[lbase + aa[u]] = cnt[u]; }
             }
         }
         {
@@ -461,9 +608,8 @@ __global__ void __launch_bounds__(256) reward_score_kernel(const uint32_t* __res
                                                            const float* __restrict__ cost, const int32_t* __restrict__ guard,
                                                            int A, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TermsS terms = carve_terms<NW>(smem_raw);
+    TermsS terms = carve_terms<NW>(smem_raw);
     stage_terms<NW>(p, size, cost, guard, A, terms);
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < B; s += (int64_t)gridDim.x * 8) {
         uint32_t w[NW];
@@ -507,7 +653,7 @@ static MctsLayout mcts_layout(int A, int T, int R) {
 
 template <int NW>
 static int launch_mcts(MctsArgs& args, int grid, cudaStream_t st) {
-    const size_t smem = terms_smem_bytes<NW>();
+    const size_t smem = mcts_smem_bytes<NW>();
     static bool attr_set_dev[64] = {};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -539,8 +685,10 @@ extern "C" int nerrf_reward_score(const uint32_t* states, int64_t B, const float
     if (g > cap) g = cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (NW == 1) reward_score_kernel<1><<<(unsigned)g, 256, terms_smem_bytes<1>(), st>>>(states, B, p, size, cost, guard, A, out);
-    else if (NW == 2) reward_score_kernel<2><<<(unsigned)g, 256, terms_smem_bytes<2>(), st>>>(states, B, p, size, cost, guard, A, out);
-    else {
+    else if (NW == 2) {                                                   // 50 / 100 KB of staged terms: above the 48 KB default
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)terms_smem_bytes<2>()));
+        reward_score_kernel<2><<<(unsigned)g, 256, terms_smem_bytes<2>(), st>>>(states, B, p, size, cost, guard, A, out);
+    } else {
         NERRF_CHECK_CUDA(cudaFuncSetAttribute(reward_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)terms_smem_bytes<4>()));
         reward_score_kernel<4><<<(unsigned)g, 256, terms_smem_bytes<4>(), st>>>(states, B, p, size, cost, guard, A, out);
     }

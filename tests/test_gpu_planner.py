@@ -51,6 +51,9 @@ CASES = [  # A, R, D, T, seed
     (4096, 1024, 50, 4, 9),          # NW = 4
     (10, 8192, 50, 12, 3),           # R >> A, D > A: rollouts exhaust the action set
     (64, 1, 5, 20, 2),               # R = 1
+    (300, 256, 100, 6, 4),           # D > 64: rollouts deeper than the rank-space path (per-step bitset updates), then <= 64 below deeper leaves
+    (2048, 512, 64, 5, 6),           # exactly 64 picks: both slot registers of the rank list full; NW = 2
+    (90, 128, 64, 10, 8),            # D = 64 with fewer actions than picks after a few levels
 ]
 
 
