@@ -268,13 +268,19 @@ def run_single(args, dev, local_rank):
     dom_ms = float(layer_ms[:, 1:LAYERS - 1].mean()) if LAYERS > 2 else float(layer_ms[:, 1:].mean())
     dom_bytes = algorithmic_bytes_layer(E, N, HIDDEN)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_l1 = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("sage_layer_F128_dram_bytes_per_launch")
+        traffic_l1 = json.load(open(tp)).get("sage_layer_F32_dram_bytes_per_launch")
+    l1_bytes = algorithmic_bytes_layer(E, N, F_IN)
+    l1_ms = float(layer_ms[:, 0].mean())
     roofline = {"bound": "hbm", "kernel": "fused GraphSAGE-T layer F=128 (gather+aggregate+GEMM)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full capture of the same kernel and graph (profiles/traffic.json); not measured in this run",
+                "layer_F32": {"kernel": "the same kernel at F=32 (layer 1, quad-mode gather)", "algorithmic_bytes_per_launch": l1_bytes,
+                              "kernel_ms": l1_ms, "achieved": l1_bytes / (l1_ms * 1e-3) / 1e9, "frac": l1_bytes / (l1_ms * 1e-3) / 1e9 / peak,
+                              "traffic": traffic_l1},
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "per_layer_ms": [float(v) for v in layer_ms.mean(0)],
                 "forward": {"algorithmic_bytes": algorithmic_bytes_forward(E, N),

@@ -284,6 +284,20 @@ int nerrf_trace_decode(const uint8_t* buf, int64_t len, int64_t n_events,
 /* NERRF_PATH_* bits for every string of a packed string column (off [n+1], data): the rule nerrf_trace_decode
  * applies to `path`, available for `new_path` (a rename target names the file from then on). */
 int nerrf_trace_path_flags(const int64_t* off, const uint8_t* data, int64_t n, uint8_t* flags_out);
+
+/* The same interning ON THE DEVICE ("inode/path dedup via hash"; architecture.mdx:39-41): identical
+ * nodes, numbering and names for the same events in the same processing order, computed by data-parallel passes (64-bit
+ * hash + open-addressing table with first-mention atomicMin, rename-alias forest, creating-mention scan).  All array
+ * arguments are DEVICE pointers (order may be NULL = stored order); n_nodes is a HOST pointer (the call synchronises the
+ * stream).  A 64-bit hash collision between two different keys is detected (keys are compared with their first mention's
+ * bytes) and reported as an error, never merged silently.  workspace: 256-byte aligned, size from
+ * nerrf_trace_intern_device_workspace_bytes. */
+int nerrf_trace_intern_device_workspace_bytes(int64_t n_events, int64_t node_capacity, int64_t* bytes);
+int nerrf_trace_intern_device(int64_t n_events, const int64_t* order, const uint32_t* pid, const int64_t* path_off,
+                              const uint8_t* path_data, const int64_t* new_path_off, const uint8_t* new_path_data,
+                              int merge_renames, int32_t* node_p, int32_t* node_f, int32_t* node_g, int64_t* n_nodes,
+                              int8_t* node_kind, int64_t* node_name_event, int8_t* node_name_which,
+                              int64_t node_capacity, void* workspace, int64_t workspace_bytes, void* stream);
 int nerrf_trace_intern(int64_t n_events, const int64_t* order, const uint32_t* pid,
                        const int64_t* path_off, const uint8_t* path_data,
                        const int64_t* new_path_off, const uint8_t* new_path_data, int merge_renames,

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libnerrf_b200.so")
-SOURCES = ["api.cu", "sage.cu", "sage_umma.cu", "sage_bwd.cu", "mcts.cu", "lstm.cu", "lstm_umma.cu", "graph.cu", "ingest.cu"]
+SOURCES = ["api.cu", "sage.cu", "sage_umma.cu", "sage_bwd.cu", "mcts.cu", "lstm.cu", "lstm_umma.cu", "graph.cu", "ingest.cu", "intern_device.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

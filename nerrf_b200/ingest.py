@@ -151,6 +151,44 @@ def intern_nodes(cols: EventColumns, order=None, merge_renames=True):
     return node_p, node_f, node_g, kind[:N].copy(), name_event[:N].copy(), name_which[:N].copy()
 
 
+def intern_nodes_device(cols: EventColumns, order=None, merge_renames=True, device="cuda", return_device=False):
+    """`intern_nodes` on the GPU (nerrf_trace_intern_device, csrc/intern_device.cu: hash table + rename-alias forest +
+    creating-mention scan): the same six arrays for the same events in the same processing order.  The pid / path /
+    new_path columns are uploaded here; return_device=True leaves node_p / node_f / node_g on the device (torch
+    tensors) for the feature / CSR kernels that consume them there."""
+    import torch
+    dev = torch.device(device)
+    n = cols.n
+    cap = max((2 if merge_renames else 3) * n, 1)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+    (poff, pdata), (goff, gdata) = cols.strings["path"], cols.strings["new_path"]
+    d_pid = up(cols.pid.view(np.int32) if cols.pid.dtype == np.uint32 else cols.pid.astype(np.uint32).view(np.int32), np.int32)
+    d_poff, d_goff = up(poff, np.int64), up(goff, np.int64)
+    d_pdata = up(pdata if pdata.size else np.zeros(1, np.uint8), np.uint8)
+    d_gdata = up(gdata if gdata.size else np.zeros(1, np.uint8), np.uint8)
+    d_order = None if order is None else up(order, np.int64)
+    node_p = torch.empty(max(n, 1), dtype=torch.int32, device=dev); node_f = torch.empty_like(node_p); node_g = torch.empty_like(node_p)
+    kind = torch.zeros(cap, dtype=torch.int8, device=dev); name_event = torch.zeros(cap, dtype=torch.int64, device=dev)
+    name_which = torch.zeros(cap, dtype=torch.int8, device=dev)
+    need = C.c_int64()
+    _lib.check(_lib.lib().nerrf_trace_intern_device_workspace_bytes(n, cap, C.byref(need)), "intern_device_workspace_bytes")
+    ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    nn = C.c_int64()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nerrf_trace_intern_device(n, _lib.ptr(d_order), _lib.ptr(d_pid), _lib.ptr(d_poff), _lib.ptr(d_pdata),
+                                                        _lib.ptr(d_goff), _lib.ptr(d_gdata), int(bool(merge_renames)),
+                                                        _lib.ptr(node_p), _lib.ptr(node_f), _lib.ptr(node_g), C.byref(nn),
+                                                        _lib.ptr(kind), _lib.ptr(name_event), _lib.ptr(name_which), cap,
+                                                        C.c_void_p(ws_ptr), need.value, _lib.current_stream_ptr()),
+                   "nerrf_trace_intern_device")
+    N = nn.value
+    host = lambda t_: t_.cpu().numpy()
+    if return_device:
+        return node_p[:n], node_f[:n], node_g[:n], host(kind[:N]), host(name_event[:N]), host(name_which[:N])
+    return host(node_p[:n]), host(node_f[:n]), host(node_g[:n]), host(kind[:N]), host(name_event[:N]), host(name_which[:N])
+
+
 def _node_names(cols, name_event, name_which):
     """pid nodes -> "pid:<pid>"; file nodes -> the path (or new_path) of the event that names them."""
     (poff, pdata), (goff, gdata) = cols.strings["path"], cols.strings["new_path"]
