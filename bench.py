@@ -622,6 +622,10 @@ def run_cfg5(dev, dist_rw, n_procs=10400, n_attacked=40):
                     "kills_correct": len(sp.killed & bad_pids), "kills_wrong": len(sp.killed - bad_pids),
                     "note": "planner spec v1: a reversion only sticks once the process that wrote the file is killed (cost 10), so the "
                             "plan interleaves process kills and file reversions; <= 32 kill candidates per tick"},
+           "stream_upload_ms": float(getattr(sp, "ingest_ms", 0.0)),
+           "constructor": "device-resident stream (nerrf_b200.stream.DeviceStream): columns uploaded once (stream_upload_ms, inside "
+                          "seconds_total); per tick the window is a slice of the time-sorted index array and node interning (hash "
+                          "table), per-node features, edge assembly and the CSR sort run on the GPU",
            "not_timed": {"train_s": t_train, "trace_generation_s": t_gen},
            "ok": True}
     return out

@@ -288,16 +288,24 @@ int nerrf_trace_path_flags(const int64_t* off, const uint8_t* data, int64_t n, u
 /* The same interning ON THE DEVICE ("inode/path dedup via hash"; architecture.mdx:39-41): identical
  * nodes, numbering and names for the same events in the same processing order, computed by data-parallel passes (64-bit
  * hash + open-addressing table with first-mention atomicMin, rename-alias forest, creating-mention scan).  All array
- * arguments are DEVICE pointers (order may be NULL = stored order); n_nodes is a HOST pointer (the call synchronises the
- * stream).  A 64-bit hash collision between two different keys is detected (keys are compared with their first mention's
+ * arguments are DEVICE pointers; n_nodes is a HOST pointer (the call synchronises the stream).  The columns hold n_stored
+ * events; the n_events events order[0..n_events) of them are processed in that order (order == NULL: the first n_events in
+ * stored order) -- a sliding window over a resident stream is a slice of its time-sorted index array.  node_p / node_f /
+ * node_g are written BY STORED INDEX (arrays of n_stored entries, only the processed events' entries are touched).  A 64-bit hash collision between two different keys is detected (keys are compared with their first mention's
  * bytes) and reported as an error, never merged silently.  workspace: 256-byte aligned, size from
  * nerrf_trace_intern_device_workspace_bytes. */
 int nerrf_trace_intern_device_workspace_bytes(int64_t n_events, int64_t node_capacity, int64_t* bytes);
-int nerrf_trace_intern_device(int64_t n_events, const int64_t* order, const uint32_t* pid, const int64_t* path_off,
+int nerrf_trace_intern_device(int64_t n_events, int64_t n_stored, const int64_t* order, const uint32_t* pid, const int64_t* path_off,
                               const uint8_t* path_data, const int64_t* new_path_off, const uint8_t* new_path_data,
                               int merge_renames, int32_t* node_p, int32_t* node_f, int32_t* node_g, int64_t* n_nodes,
                               int8_t* node_kind, int64_t* node_name_event, int8_t* node_name_which,
                               int64_t node_capacity, void* workspace, int64_t workspace_bytes, void* stream);
+/* hash_out[v] = 64-bit hash of node v's NAME (the path / new_path of its naming event; pid nodes: the pid), device arrays:
+ * lets a caller match nodes against a set of names without moving the strings (nerrf_b200/ingest.py name_hash is the same
+ * function on the host). */
+int nerrf_trace_name_hash(int64_t n_nodes, const int64_t* node_name_event, const int8_t* node_name_which,
+                          const uint32_t* pid, const int64_t* path_off, const uint8_t* path_data,
+                          const int64_t* new_path_off, const uint8_t* new_path_data, uint64_t* hash_out, void* stream);
 int nerrf_trace_intern(int64_t n_events, const int64_t* order, const uint32_t* pid,
                        const int64_t* path_off, const uint8_t* path_data,
                        const int64_t* new_path_off, const uint8_t* new_path_data, int merge_renames,

@@ -68,8 +68,9 @@ SIGNATURES = {
     "nerrf_trace_decode": (C.c_int, [vp, C.c_int64, C.c_int64] + [vp] * 17),
     "nerrf_trace_path_flags": (C.c_int, [vp, vp, C.c_int64, vp]),
     "nerrf_trace_intern_device_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
-    "nerrf_trace_intern_device": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64),
+    "nerrf_trace_intern_device": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64),
                                             vp, vp, vp, C.c_int64, vp, C.c_int64, vp]),
+    "nerrf_trace_name_hash": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nerrf_trace_intern": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64),
                                      vp, vp, vp, C.c_int64]),
 }

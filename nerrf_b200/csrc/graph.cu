@@ -13,7 +13,9 @@
 // rowptr from the dst boundaries of the sorted keys (no atomics anywhere: the result is deterministic).
 // String work (path/inode dedup, feature counts) stays on the host: nerrf_b200/graph.py graph_from_events.
 #include "common.cuh"
+#include "radix_sort.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 
 namespace nerrf {
 
@@ -28,6 +30,10 @@ __global__ void __launch_bounds__(256) csr_keys_kernel(const int32_t* __restrict
         if ((uint32_t)d >= (uint64_t)N || (uint32_t)s >= (uint64_t)N) { *bad = 1; d = 0; }   // keep the later passes in range
         const uint32_t b = __float_as_uint(t[i] + 0.0f);                 // -0.0 -> +0.0: they compare equal on the host
         const uint32_t ord = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);   // monotone float -> uint
+        if (i > 0) {                                                     // time order of the input (see the sort below)
+            const uint32_t bp = __float_as_uint(t[i - 1] + 0.0f);
+            if ((bp ^ ((bp >> 31) ? 0xffffffffu : 0x80000000u)) > ord) bad[1] = 1;
+        }
         keys[i] = ((uint64_t)(uint32_t)d << 32) | ord;
         vals[i] = (uint32_t)i;
     }
@@ -206,7 +212,8 @@ static int csr_layout(int64_t E, int64_t N, CsrWs* L) {
     L->vals_a = o; o += up256((size_t)E * 4);
     L->vals_b = o; o += up256((size_t)E * 4);
     L->bad = o;    o += 256;
-    L->temp = o;   o += up256(temp);
+    const size_t own = rs_scratch_bytes(E > 0 ? E : 1);
+    L->temp = o;   o += up256(temp > own ? temp : own);
     L->temp_bytes = temp;
     L->total = o;
     return NERRF_OK;
@@ -255,19 +262,37 @@ extern "C" int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, con
     uint64_t* ka = (uint64_t*)(ws + L.keys_a); uint64_t* kb = (uint64_t*)(ws + L.keys_b);
     uint32_t* va = (uint32_t*)(ws + L.vals_a); uint32_t* vb = (uint32_t*)(ws + L.vals_b);
     int* bad = (int*)(ws + L.bad);
-    NERRF_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+    NERRF_CHECK_CUDA(cudaMemsetAsync(bad, 0, 8, st));
     csr_keys_kernel<<<grid, 256, 0, st>>>(src, dst, t, n_edges, n_nodes, ka, va, bad);
     rc = launch_status("csr_keys_kernel");
     if (rc != NERRF_OK) return rc;
-    cub::DoubleBuffer<uint64_t> k(ka, kb);
-    cub::DoubleBuffer<uint32_t> v(va, vb);
-    size_t temp = L.temp_bytes;
-    NERRF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.temp, temp, k, v, n_edges, 0, key_bits(n_nodes), st));
+    // the sort: our own stable LSD radix sort (radix_sort.cuh); cub::DeviceRadixSort is kept selectable for comparison
+    // (NERRF_GRAPH_SORT=cub) and for edge lists of 2^31 pairs and more (our scatter offsets are 32-bit)
+    static const bool want_cub = [] { const char* e = getenv("NERRF_GRAPH_SORT"); return e && e[0] == 'c'; }();
+    const uint64_t* ks; const uint32_t* vs;
+    if (want_cub || n_edges >= ((int64_t)1 << 31)) {
+        cub::DoubleBuffer<uint64_t> k(ka, kb);
+        cub::DoubleBuffer<uint32_t> v(va, vb);
+        size_t temp = L.temp_bytes;
+        NERRF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.temp, temp, k, v, n_edges, 0, key_bits(n_nodes), st));
+        ks = k.Current(); vs = v.Current();
+    } else {
+        // an edge list that already is in time order (an event stream is) only needs the stable sort by destination: the
+        // low 32 key bits (the time) are skipped -- 3 passes instead of 7 at 2^20 nodes.  `bad[1]` was set by csr_keys_kernel
+        // if any edge is older than its predecessor.
+        int h_unsorted = 1;
+        NERRF_CHECK_CUDA(cudaMemcpyAsync(&h_unsorted, bad + 1, 4, cudaMemcpyDeviceToHost, st));
+        NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
+        const int which = radix_sort_pairs(ka, kb, va, vb, n_edges, h_unsorted ? 0 : 32, key_bits(n_nodes), ws + L.temp, st);
+        ks = which ? kb : ka; vs = which ? vb : va;
+        rc = launch_status("radix sort");
+        if (rc != NERRF_OK) return rc;
+    }
     if (rowptr_is64)
-        csr_finish_kernel<int64_t><<<grid, 256, 0, st>>>(k.Current(), v.Current(), src, t, conf, n_edges, n_nodes, t_ref, tau,
+        csr_finish_kernel<int64_t><<<grid, 256, 0, st>>>(ks, vs, src, t, conf, n_edges, n_nodes, t_ref, tau,
                                                          (int64_t*)rowptr_out, col_out, ew_out);
     else
-        csr_finish_kernel<int32_t><<<grid, 256, 0, st>>>(k.Current(), v.Current(), src, t, conf, n_edges, n_nodes, t_ref, tau,
+        csr_finish_kernel<int32_t><<<grid, 256, 0, st>>>(ks, vs, src, t, conf, n_edges, n_nodes, t_ref, tau,
                                                          (int32_t*)rowptr_out, col_out, ew_out);
     rc = launch_status("csr_finish_kernel");
     if (rc != NERRF_OK) return rc;

@@ -19,6 +19,7 @@
 //
 // Bound: HBM / L2 latency of the table probes; ~100 B of traffic per event.  No string ever goes back to the host.
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace nerrf {
 namespace {
@@ -67,7 +68,8 @@ __device__ __forceinline__ int32_t table_insert(const Table t, uint64_t h, int32
 }
 
 struct InternArgs {
-    int64_t n;
+    int64_t n;                             // events processed (ranks 0..n-1)
+    int64_t n_total;                       // events stored (the columns' length): order[] indexes into [0, n_total)
     const int64_t* order;                  // processing order: rank k handles stored event order[k] (NULL: identity)
     const uint32_t* pid;
     const int64_t *path_off, *gpath_off;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256) intern_hash_kernel(InternArgs a) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += stride) {
         const int64_t i = stored(a, k);
-        if (i < 0 || i >= a.n) { *a.err = 4; a.slot_p[k] = a.slot_f[k] = 0; a.slot_g[k] = -1; continue; }
+        if (i < 0 || i >= a.n_total) { *a.err = 4; a.slot_p[k] = a.slot_f[k] = 0; a.slot_g[k] = -1; continue; }
         const int32_t sp = table_insert(a.pids, mix64((uint64_t)a.pid[i] + 0x9E3779B97F4A7C15ull), (int32_t)k);
         const uint8_t* s = a.path_data + a.path_off[i];
         const int64_t n = a.path_off[i + 1] - a.path_off[i];
@@ -161,59 +163,6 @@ __global__ void __launch_bounds__(256) intern_flags_kernel(InternArgs a) {
     }
 }
 
-// ---- exclusive scan of int32 [m] in place: per-block (1024 elements) scan + block sums, scan of the sums, add
-constexpr int SCAN_TILE = 1024;
-__global__ void __launch_bounds__(256) scan_tiles_kernel(int32_t* __restrict__ v, int64_t m, int32_t* __restrict__ sums) {
-    __shared__ int32_t warp_tot[8];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    int32_t x[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = (base + k < m) ? v[base + k] : 0;
-    const int32_t mine = x[0] + x[1] + x[2] + x[3];
-    int32_t inc = mine;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    int32_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-    int32_t run = wbase + inc - mine;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { if (base + k < m) v[base + k] = run; run += x[k]; }
-    if (threadIdx.x == 255) sums[blockIdx.x] = wbase + inc;
-}
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t* __restrict__ sums, int64_t nb, int32_t* __restrict__ total) {
-    __shared__ int32_t warp_tot[32];
-    __shared__ int32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
-        const int64_t i = b0 + threadIdx.x;
-        const int32_t x = i < nb ? sums[i] : 0;
-        int32_t inc = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        int32_t wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-        const int32_t carry = carry_s;
-        if (i < nb) sums[i] = carry + wbase + inc - x;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + wbase + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry_s;
-}
-__global__ void __launch_bounds__(256) scan_add_kernel(int32_t* __restrict__ v, int64_t m, const int32_t* __restrict__ sums) {
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    const int32_t add = sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (base + k < m) v[base + k] += add;
-}
-
 // node id of the node made by creating mention c (index into the [3n] scan)
 __global__ void __launch_bounds__(256) intern_assign_kernel(InternArgs a, const int32_t* __restrict__ total) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -259,6 +208,26 @@ __global__ void __launch_bounds__(256) intern_names_kernel(InternArgs a, const i
     }
 }
 
+// 64-bit hash of every node's NAME (the string its naming event gives it; pid nodes: their pid): lets a caller match
+// nodes against a set of names (e.g. the files an earlier tick already reverted) without bringing a million strings
+// to the host.  Same function as nerrf_b200/ingest.py name_hash.
+__global__ void __launch_bounds__(256) name_hash_kernel(int64_t n_nodes, const int64_t* __restrict__ name_event,
+                                                        const int8_t* __restrict__ name_which, const uint32_t* __restrict__ pid,
+                                                        const int64_t* __restrict__ path_off, const uint8_t* __restrict__ path_data,
+                                                        const int64_t* __restrict__ gpath_off, const uint8_t* __restrict__ gpath_data,
+                                                        unsigned long long* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += stride) {
+        const int64_t e = name_event[v];
+        const int w = name_which[v];
+        unsigned long long h;
+        if (w == 2) h = mix64((uint64_t)pid[e] + 0x9E3779B97F4A7C15ull);
+        else if (w == 1) h = hash_bytes(gpath_data + gpath_off[e], gpath_off[e + 1] - gpath_off[e]);
+        else h = hash_bytes(path_data + path_off[e], path_off[e + 1] - path_off[e]);
+        out[v] = h;
+    }
+}
+
 struct InternWs {
     size_t fkey, ffirst, pkey, pfirst, slot_p, slot_f, slot_g, flags, sums, total, err, name_code, bytes;
     uint32_t fcap, pcap;
@@ -300,7 +269,7 @@ extern "C" int nerrf_trace_intern_device_workspace_bytes(int64_t n_events, int64
     return NERRF_OK;
 }
 
-extern "C" int nerrf_trace_intern_device(int64_t n_events, const int64_t* order, const uint32_t* pid, const int64_t* path_off, const uint8_t* path_data,
+extern "C" int nerrf_trace_intern_device(int64_t n_events, int64_t n_stored, const int64_t* order, const uint32_t* pid, const int64_t* path_off, const uint8_t* path_data,
                                          const int64_t* new_path_off, const uint8_t* new_path_data, int merge_renames,
                                          int32_t* node_p, int32_t* node_f, int32_t* node_g, int64_t* n_nodes, int8_t* node_kind,
                                          int64_t* node_name_event, int8_t* node_name_which, int64_t node_capacity,
@@ -309,6 +278,7 @@ extern "C" int nerrf_trace_intern_device(int64_t n_events, const int64_t* order,
     *n_nodes = 0;
     if (n_events == 0) return NERRF_OK;
     NERRF_REQUIRE(n_events > 0 && n_events < ((int64_t)1 << 29), "n_events=%lld out of range", (long long)n_events);
+    NERRF_REQUIRE(n_stored >= n_events || (order && n_stored >= 1), "n_stored=%lld < n_events without an order", (long long)n_stored);
     NERRF_REQUIRE(pid && path_off && path_data && new_path_off && new_path_data && node_p && node_f && node_g && node_kind &&
                       node_name_event && node_name_which && workspace,
                   "null pointer");
@@ -319,7 +289,7 @@ extern "C" int nerrf_trace_intern_device(int64_t n_events, const int64_t* order,
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     InternArgs a;
-    a.n = n_events; a.order = order; a.pid = pid; a.path_off = path_off; a.gpath_off = new_path_off; a.path_data = path_data; a.gpath_data = new_path_data;
+    a.n = n_events; a.n_total = n_stored; a.order = order; a.pid = pid; a.path_off = path_off; a.gpath_off = new_path_off; a.path_data = path_data; a.gpath_data = new_path_data;
     a.merge = merge_renames ? 1 : 0;
     a.files.key = (unsigned long long*)(ws + L.fkey); a.files.first = (int32_t*)(ws + L.ffirst); a.files.mask = L.fcap - 1;
     a.pids.key = (unsigned long long*)(ws + L.pkey); a.pids.first = (int32_t*)(ws + L.pfirst); a.pids.mask = L.pcap - 1;
@@ -340,9 +310,7 @@ extern "C" int nerrf_trace_intern_device(int64_t n_events, const int64_t* order,
     intern_verify_kernel<<<grid, 256, 0, st>>>(a);
     intern_flags_kernel<<<grid, 256, 0, st>>>(a);
     const int64_t m = 3 * n_events;
-    scan_tiles_kernel<<<(unsigned)L.nb, 256, 0, st>>>(a.flags, m, sums);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, L.nb, total);
-    scan_add_kernel<<<(unsigned)L.nb, 256, 0, st>>>(a.flags, m, sums);
+    exclusive_scan_i32(a.flags, m, sums, total, st);
     intern_assign_kernel<<<grid, 256, 0, st>>>(a, total);
     intern_names_kernel<<<grid, 256, 0, st>>>(a, total);
     int rc = launch_status("device interning kernels");
@@ -351,10 +319,22 @@ extern "C" int nerrf_trace_intern_device(int64_t n_events, const int64_t* order,
     NERRF_CHECK_CUDA(cudaMemcpyAsync(&h[0], total, 4, cudaMemcpyDeviceToHost, st));
     NERRF_CHECK_CUDA(cudaMemcpyAsync(&h[1], a.err, 4, cudaMemcpyDeviceToHost, st));
     NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
-    NERRF_REQUIRE(h[1] != 4, "order[] holds an index outside [0, n_events)");
+    NERRF_REQUIRE(h[1] != 4, "order[] holds an index outside [0, n_stored)");
     NERRF_REQUIRE(h[1] != 1, "interning table full (internal sizing error)");
     NERRF_REQUIRE(h[1] != 2, "64-bit hash collision between two different paths: use the host interning for this batch");
     NERRF_REQUIRE(h[1] != 3 && h[0] <= node_capacity, "node_capacity=%lld too small (%d nodes)", (long long)node_capacity, h[0]);
     *n_nodes = h[0];
     return NERRF_OK;
+}
+
+extern "C" int nerrf_trace_name_hash(int64_t n_nodes, const int64_t* node_name_event, const int8_t* node_name_which,
+                                     const uint32_t* pid, const int64_t* path_off, const uint8_t* path_data,
+                                     const int64_t* new_path_off, const uint8_t* new_path_data, uint64_t* hash_out, void* stream) {
+    NERRF_REQUIRE(n_nodes >= 0, "negative node count");
+    if (n_nodes == 0) return NERRF_OK;
+    NERRF_REQUIRE(node_name_event && node_name_which && pid && path_off && path_data && new_path_off && new_path_data && hash_out,
+                  "null pointer");
+    name_hash_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(n_nodes, node_name_event, node_name_which, pid, path_off, path_data,
+                                                                        new_path_off, new_path_data, (unsigned long long*)hash_out);
+    return launch_status("name_hash_kernel");
 }

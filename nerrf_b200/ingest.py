@@ -176,7 +176,7 @@ def intern_nodes_device(cols: EventColumns, order=None, merge_renames=True, devi
     ws_ptr = (ws.data_ptr() + 255) & ~255
     nn = C.c_int64()
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().nerrf_trace_intern_device(n, _lib.ptr(d_order), _lib.ptr(d_pid), _lib.ptr(d_poff), _lib.ptr(d_pdata),
+        _lib.check(_lib.lib().nerrf_trace_intern_device(n, n, _lib.ptr(d_order), _lib.ptr(d_pid), _lib.ptr(d_poff), _lib.ptr(d_pdata),
                                                         _lib.ptr(d_goff), _lib.ptr(d_gdata), int(bool(merge_renames)),
                                                         _lib.ptr(node_p), _lib.ptr(node_f), _lib.ptr(node_g), C.byref(nn),
                                                         _lib.ptr(kind), _lib.ptr(name_event), _lib.ptr(name_which), cap,
@@ -288,8 +288,6 @@ def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, o
     """Per-file event sequences for the LSTM without per-event Python: the same arrays as
     pipeline.file_sequences(events_from_columns(cols), graph) -- seq fp32 [n_files, t_max, 16], lengths int32, node ids --
     (the last t_max events of every file node, oldest first; feature layout: pipeline.file_sequences)."""
-    from .ai.models import lstm
-    t_max = t_max or lstm.T_MAX
     cols = resolve_columns(cols)
     n = cols.n
     ts = cols.timestamp
@@ -297,17 +295,25 @@ def sequences_from_columns(cols: EventColumns, merge_renames=True, t_max=None, o
     t0 = float(ts[order[0]]) if n else 0.0
     span = max(float(ts[order[-1]]) - t0, 1e-6) if n else 1.0
     _, node_f, _, kind, _, _ = intern_nodes(cols, order, merge_renames)
-    F = node_f[order].astype(np.int64)
-    tt = ts[order]                                        # absolute seconds, time-sorted
+    return sequences_core(cols, order, node_f[order].astype(np.int64), ts[order], t0, span, kind.shape[0], t_max, observable, only_nodes)
+
+
+def sequences_core(cols: EventColumns, order, F, tt, t0, span, n_nodes, t_max=None, observable=False, only_nodes=None):
+    """The sequence builder proper, on already interned events: `order` = stored indices of the events in time order,
+    F = their file node ids, tt = their absolute timestamps (both in that order).  Used by sequences_from_columns and by the
+    device stream (stream.DeviceStream), whose interning ran on the GPU."""
+    from .ai.models import lstm
+    t_max = t_max or lstm.T_MAX
+    n = int(F.shape[0])
     if only_nodes is not None:
         # sequences for a subset of the file nodes only (the top-A candidates of a large window): drop every other event
         # up front -- node ids, time order and the per-file histories of the kept nodes are unchanged
-        keep_node = np.zeros(kind.shape[0], bool); keep_node[np.asarray(only_nodes, np.int64)] = True
+        keep_node = np.zeros(n_nodes, bool); keep_node[np.asarray(only_nodes, np.int64)] = True
         sel_ev = keep_node[F]
         order, F, tt = order[sel_ev], F[sel_ev], tt[sel_ev]
         n = int(F.shape[0])
-        if n == 0:
-            return np.zeros((0, t_max, lstm.D_IN), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int64)
+    if n == 0:
+        return np.zeros((0, t_max, lstm.D_IN), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int64)
     # group by file node, keeping time order inside a group
     by_file = np.argsort(F, kind="stable")
     Fg = F[by_file]

@@ -117,6 +117,159 @@ def window(cols: ingest.EventColumns, t_lo: float, t_hi: float) -> ingest.EventC
     return ingest.EventColumns(n=int(keep.shape[0]), strings=strings, **sc)
 
 
+# ---------------------------------------------------------------------------------------------- device-resident stream
+_M64 = (1 << 64) - 1
+
+
+def _mix64(h: int) -> int:
+    h ^= h >> 33; h = (h * 0xff51afd7ed558ccd) & _M64; h ^= h >> 33; h = (h * 0xc4ceb9fe1a85ec53) & _M64; h ^= h >> 33
+    return h or 1
+
+
+def name_hash(name) -> int:
+    """The 64-bit name hash of csrc/intern_device.cu (nerrf_trace_name_hash) on the host, as a SIGNED int64: FNV-1a over
+    the bytes seeded with the length, murmur3 finaliser; "pid:<n>" names hash their pid."""
+    if isinstance(name, str) and name.startswith("pid:") and name[4:].isdigit():
+        h = _mix64((int(name[4:]) + 0x9E3779B97F4A7C15) & _M64)
+    else:
+        b = name.encode("utf-8") if isinstance(name, str) else bytes(name)
+        h = (0xcbf29ce484222325 ^ len(b)) & _M64
+        for c in b:
+            h = ((h ^ c) * 0x100000001b3) & _M64
+        h = _mix64(h)
+    return h - (1 << 64) if h >= (1 << 63) else h
+
+
+class LazyNames:
+    """Node names of a window graph, decoded on demand (a window holds ~10^6 nodes, a plan names a few thousand)."""
+
+    def __init__(self, cols: ingest.EventColumns, name_event: np.ndarray, name_which: np.ndarray):
+        self.cols, self.name_event, self.name_which = cols, name_event, name_which
+
+    def __len__(self):
+        return int(self.name_event.shape[0])
+
+    def __getitem__(self, v):
+        e, w = int(self.name_event[v]), int(self.name_which[v])
+        return "pid:%d" % int(self.cols.pid[e]) if w == 2 else self.cols.text("path" if w == 0 else "new_path", e)
+
+
+class DeviceStream:
+    """The event stream resident in HBM ("window, inode/path dedup via hash, sort-by-dst -> CSR,
+    feature counts" on the GPU; docs/content/docs/architecture.mdx:39-41).  Columns are uploaded ONCE; a sliding window
+    is a slice of the time-sorted index array, and everything per tick -- node interning (hash table), per-node features,
+    edge assembly, CSR -- runs on the device.  The host keeps the strings only to NAME the few nodes a plan touches."""
+
+    def __init__(self, cols: ingest.EventColumns, device="cuda", observable=True, merge_renames=True):
+        import torch
+        self.torch = torch
+        cols = ingest.resolve_columns(cols)                   # path-less (write) events follow the pid's open file
+        self.cols, self.observable, self.merge = cols, observable, bool(merge_renames)
+        self.dev = dev = torch.device(device)
+        ts = cols.timestamp
+        self.order = np.argsort(ts, kind="stable")
+        self.ts_sorted = ts[self.order]
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+        n = cols.n
+        self.n = n
+        (poff, pdata), (goff, gdata) = cols.strings["path"], cols.strings["new_path"]
+        self.d_order = up(self.order, np.int64)
+        self.d_ts = up(ts, np.float64)
+        self.d_pid = up(cols.pid.astype(np.uint32).view(np.int32), np.int32)
+        self.d_poff, self.d_goff = up(poff, np.int64), up(goff, np.int64)
+        self.d_pdata = up(pdata if pdata.size else np.zeros(1, np.uint8), np.uint8)
+        self.d_gdata = up(gdata if gdata.size else np.zeros(1, np.uint8), np.uint8)
+        raw = cols.event_slot
+        self.d_raw_slot = up(raw, np.uint8)
+        self.d_slot = up(np.asarray(G.OBSERVABLE_SLOT, np.uint8)[raw] if observable else raw, np.uint8)
+        self.d_bytes = up(cols.bytes.astype(np.int64), np.int64)
+        pf = cols.path_flags
+        if self.merge:                                        # the renamed twin is the same node: its .lockbit bit counts
+            pf = pf | (ingest.path_flags_of(goff, gdata) & np.uint8(1))
+        self.d_pf = up(pf, np.uint8)
+        self.cap = max((2 if self.merge else 3) * n, 1)
+        self.node_p = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.node_f = torch.empty_like(self.node_p); self.node_g = torch.empty_like(self.node_p)
+        self.kind = torch.zeros(self.cap, dtype=torch.int8, device=dev)
+        self.name_event = torch.zeros(self.cap, dtype=torch.int64, device=dev)
+        self.name_which = torch.zeros(self.cap, dtype=torch.int8, device=dev)
+        import ctypes as C
+        from . import _lib
+        need = C.c_int64()
+        _lib.check(_lib.lib().nerrf_trace_intern_device_workspace_bytes(max(n, 1), self.cap, C.byref(need)), "intern_device_workspace_bytes")
+        self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+        self._ws_bytes = need.value
+
+    def span(self):
+        return float(self.ts_sorted[0]), float(self.ts_sorted[-1])
+
+    def window_graph(self, t_lo: float, t_hi: float, window_s: float):
+        """The temporal graph of the events with t_lo < t <= t_hi (device tensors), or None when there are none.
+        Same construction as ingest.graph_from_columns(stream.window(cols, t_lo, t_hi), device=...)."""
+        import ctypes as C
+        from . import _lib
+        torch = self.torch
+        lo = int(np.searchsorted(self.ts_sorted, t_lo, "right")); hi = int(np.searchsorted(self.ts_sorted, t_hi, "right"))
+        nw = hi - lo
+        if nw <= 0:
+            return None
+        sel = self.d_order[lo:hi]                                   # the window = a slice of the time-sorted index array
+        nn = C.c_int64()
+        ws_ptr = (self._ws.data_ptr() + 255) & ~255
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().nerrf_trace_intern_device(
+                nw, self.n, _lib.ptr(sel), _lib.ptr(self.d_pid), _lib.ptr(self.d_poff), _lib.ptr(self.d_pdata), _lib.ptr(self.d_goff),
+                _lib.ptr(self.d_gdata), int(self.merge), _lib.ptr(self.node_p), _lib.ptr(self.node_f), _lib.ptr(self.node_g),
+                C.byref(nn), _lib.ptr(self.kind), _lib.ptr(self.name_event), _lib.ptr(self.name_which), self.cap,
+                C.c_void_p(ws_ptr), self._ws_bytes, _lib.current_stream_ptr()), "nerrf_trace_intern_device")
+        N = int(nn.value)
+        t0 = float(self.ts_sorted[lo]); span = max(float(self.ts_sorted[hi - 1]) - t0, 1e-6)
+        window = window_s or max(span, G.WINDOW)
+        P, F = self.node_p[sel], self.node_f[sel]                   # by rank: the window's events in time order
+        t = self.d_ts[sel] - t0
+        kind_d = self.kind[:N].contiguous()
+        Gn = None
+        if not self.merge:
+            Gn = self.node_g[sel]
+            if not bool((Gn >= 0).any()):
+                Gn = None
+        x, label, size_mb = G.node_features_device(P, F, Gn, t, self.d_slot[sel], self.d_bytes[sel], self.d_pf[sel], kind_d, window)
+        tt = t.to(torch.float32)
+        if Gn is None:                                              # edges in the host loader's per-event order: p->f, f->p
+            src = torch.stack([P, F], 1).reshape(-1); dst = torch.stack([F, P], 1).reshape(-1)
+            te = tt.repeat_interleave(2)
+        else:                                                       # [, f->g, g->f]
+            keep = torch.stack([torch.ones_like(P, dtype=torch.bool)] * 2 + [Gn >= 0] * 2, 1).reshape(-1)
+            src = torch.stack([P, F, F, Gn], 1).reshape(-1)[keep]; dst = torch.stack([F, P, Gn, F], 1).reshape(-1)[keep]
+            te = tt.repeat_interleave(4)[keep]
+        rowptr, col, ew = G.build_csr_device(src.contiguous(), dst.contiguous(), te.contiguous(), torch.ones_like(te), N,
+                                             t_ref=float(span), tau=G.TAU)
+        lab = label
+        if self.observable:                                         # the kernel saw the folded slots: labels come from the annotations
+            raw = self.d_raw_slot[sel]
+            lab = (torch.bincount(F[(raw == 1) | (raw == 2)].long(), minlength=N) > 0)
+        nh = torch.empty(N, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().nerrf_trace_name_hash(N, _lib.ptr(self.name_event), _lib.ptr(self.name_which), _lib.ptr(self.d_pid),
+                                                        _lib.ptr(self.d_poff), _lib.ptr(self.d_pdata), _lib.ptr(self.d_goff),
+                                                        _lib.ptr(self.d_gdata), _lib.ptr(nh), _lib.current_stream_ptr()),
+                       "nerrf_trace_name_hash")
+        meta = {"kind": "trace", "names": LazyNames(self.cols, self.name_event[:N].cpu().numpy(), self.name_which[:N].cpu().numpy()),
+                "node_kind": kind_d.cpu().numpy().astype(np.int64), "t0": t0, "span": span, "merge_renames": self.merge,
+                "label": lab.cpu().numpy().astype(np.int64), "size_mb": size_mb.cpu().numpy(), "device": str(self.dev),
+                "name_hash": nh, "events": nw, "window_ranks": (lo, hi)}
+        return G.TemporalGraph(rowptr, col, ew, x, meta)
+
+    def sequences(self, g: G.TemporalGraph, only_nodes):
+        """LSTM sequences of the given file nodes of window graph `g` (ingest.sequences_core on the window's events)."""
+        lo, hi = g.meta["window_ranks"]
+        order = self.order[lo:hi]
+        if "_F_host" not in g.meta:
+            g.meta["_F_host"] = self.node_f[self.d_order[lo:hi]].cpu().numpy().astype(np.int64)
+        return ingest.sequences_core(self.cols, order, g.meta["_F_host"], self.ts_sorted[lo:hi], g.meta["t0"], g.meta["span"],
+                                     g.num_nodes, None, self.observable, only_nodes)
+
+
 @dataclass
 class TickResult:
     t_hi: float
@@ -146,6 +299,8 @@ class StreamingPlanner:
     device: str = "cuda"
     dist_ctx: object = None        # pipeline.DistContext for the multi-GPU form
     reverted: set = field(default_factory=set)
+    _reverted_hash: set = field(default_factory=set)
+    ingest_ms: float = 0.0         # one-time: stream columns -> HBM (DeviceStream)
     killed: set = field(default_factory=set)
     ticks: list = field(default_factory=list)
 
@@ -171,9 +326,15 @@ class StreamingPlanner:
                 buf = t.to(dev).contiguous() if lead else torch.empty(shape, device=dev, dtype=dtype)
                 dist.broadcast(buf, 0)
                 return buf
+        ds = None
         if lead:
-            ts = cols.timestamp
-            span = torch.tensor([float(ts.min()), float(ts.max())], dtype=torch.float64, device=dev)
+            # the stream becomes device resident ONCE (in production: batch by batch as the tracker delivers it); from here
+            # on a tick touches no string on the host except the names of the nodes its plan reverts
+            a = time.perf_counter()
+            ds = DeviceStream(cols, self.device, observable=True)
+            torch.cuda.synchronize()
+            self.ingest_ms = (time.perf_counter() - a) * 1e3
+            span = torch.tensor(list(ds.span()), dtype=torch.float64, device=dev)
         else:
             span = torch.zeros(2, dtype=torch.float64, device=dev)
         if multi:
@@ -183,19 +344,18 @@ class StreamingPlanner:
         while t_hi < t1:
             t_hi = min(t_hi + self.tick_s, t1)
             tm = {}
-            names, w, n_events = None, None, 0
+            names, g, n_events = None, None, 0
+            a = time.perf_counter()
             if lead:
-                a = time.perf_counter()
-                w = window(cols, t_hi - self.window_s, t_hi)
-                tm["window"] = (time.perf_counter() - a) * 1e3
-                n_events = w.n
+                # window = a slice of the time-sorted index array; interning (hash table), features, edges, CSR on the GPU
+                g = ds.window_graph(t_hi - self.window_s, t_hi, self.window_s)
+                torch.cuda.synchronize()
+                n_events = g.meta["events"] if g is not None else 0
             if multi:
                 ne = torch.tensor([n_events], device=dev); dist.broadcast(ne, 0); n_events = int(ne)
             if n_events == 0:
                 continue
-            a = time.perf_counter()
             if lead:
-                g = ingest.graph_from_columns(w, device=self.device, observable=True, window=self.window_s)
                 names = g.meta["names"]
             if multi:                                      # the device graph travels over NVLink; the strings do not
                 x = bcast(g.x if lead else None, dtype=torch.float32)
@@ -211,9 +371,9 @@ class StreamingPlanner:
             nodes = np.nonzero(kind == 0)[0]
 
             # LSTM sequences are built lazily, for the top-A candidates only (a window holds ~10^6 file nodes)
-            def seq(cand, w=w):
+            def seq(cand, g=g):
                 if lead:
-                    sq, ln, have = ingest.sequences_from_columns(w, observable=True, only_nodes=cand)
+                    sq, ln, have = ds.sequences(g, cand)
                 if multi:
                     sq_t = bcast(torch.from_numpy(sq) if lead else None, dtype=torch.float32)
                     ln_t = bcast(torch.from_numpy(ln) if lead else None, dtype=torch.int32)
@@ -226,8 +386,9 @@ class StreamingPlanner:
                 # a planning pass proposes at most 32 process kills (planner spec v1: guards live in state word 0); a tick
                 # with more suspicious processes than that plans again over what is still unreverted
                 skip = None
-                if lead and self.reverted:
-                    skip = np.asarray([names[n] in self.reverted for n in nodes.tolist()], bool)
+                if lead and self.reverted:               # files already reverted by an earlier tick: matched by name hash on the device
+                    rh = torch.tensor(sorted(self._reverted_hash), dtype=torch.int64, device=dev)
+                    skip = torch.isin(g.meta["name_hash"][torch.from_numpy(nodes).to(dev)], rh).cpu().numpy()
                 if multi:
                     flag = torch.tensor([1 if (lead and skip is not None) else 0], device=dev); dist.broadcast(flag, 0)
                     if int(flag):
@@ -241,8 +402,10 @@ class StreamingPlanner:
                 got = []
                 if lead:
                     self.killed.update(names[n] for n in res.plan_nodes if kind[n] == 1)
-                    got = [names[n] for n in res.plan_nodes if kind[n] == 0 and names[n] not in self.reverted]
+                    got = [names[n] for n in res.plan_nodes if kind[n] == 0]
+                    got = [nm for nm in dict.fromkeys(got) if nm not in self.reverted]
                     self.reverted.update(got)
+                    self._reverted_hash.update(name_hash(nm) for nm in got)
                     new += got
                 more = bool(self.kill_candidates and res.n_kill >= 32 and got)
                 if multi:

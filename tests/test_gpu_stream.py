@@ -39,3 +39,33 @@ def test_streamed_fleet_trace_plans_the_reversions(models, kills):
         assert len(sp.killed) >= len(bad) - 1                     # ... and (nearly) all of them
     else:
         assert not sp.killed
+
+
+def test_device_stream_window_equals_the_columnar_constructor():
+    """stream.DeviceStream.window_graph (columns resident in HBM, interning + features + edges + CSR on the GPU) builds
+    the same graph as ingest.graph_from_columns over stream.window(...): node numbering, CSR, labels, names, name hashes;
+    sequences of a node subset equal ingest.sequences_from_columns."""
+    from nerrf_b200 import ingest
+    cols, enc = stream.fleet_columns(60, 4, seed=3)
+    ds = stream.DeviceStream(cols, "cuda", observable=True)
+    t0, t1 = ds.span()
+    for (lo, hi) in [(t0 - 1, t0 + 30), (t0 + 10, t0 + 70), (t0 + 40, t1), (t1 + 5, t1 + 9)]:
+        g = ds.window_graph(lo, hi, 60.0)
+        w = stream.window(cols, lo, hi)
+        if w.n == 0:
+            assert g is None
+            continue
+        want = ingest.graph_from_columns(w, device="cuda", observable=True, window=60.0)
+        assert g.num_nodes == want.num_nodes and torch.equal(g.rowptr, want.rowptr) and torch.equal(g.col, want.col)
+        assert torch.allclose(g.ew, want.ew, rtol=1e-6, atol=0) and torch.allclose(g.x, want.x, rtol=1e-6, atol=1e-7)
+        assert np.array_equal(g.meta["label"], want.meta["label"]) and np.array_equal(g.meta["node_kind"], want.meta["node_kind"])
+        assert np.allclose(g.meta["size_mb"], want.meta["size_mb"])
+        names = g.meta["names"]
+        pick = np.random.default_rng(0).integers(0, g.num_nodes, 200)
+        assert [names[int(v)] for v in pick] == [want.meta["names"][int(v)] for v in pick]
+        nh = g.meta["name_hash"].cpu().numpy()
+        assert all(int(nh[int(v)]) == stream.name_hash(names[int(v)]) for v in pick[:50])
+        files = np.nonzero(g.meta["node_kind"] == 0)[0][::7]
+        sq, ln, have = ds.sequences(g, files)
+        sq2, ln2, have2 = ingest.sequences_from_columns(w, observable=True, only_nodes=files)
+        assert np.array_equal(have, have2) and np.array_equal(ln, ln2) and np.array_equal(sq, sq2)
