@@ -85,11 +85,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("NERRF_LIB", LIB_PATH)                # experiment builds of the same library (scripts/)
+    if not os.path.exists(path):
         raise NerrfError(
             f"{LIB_PATH} not found: build it with `python -m nerrf_b200.build` "
             "(nvcc, sm_100a).  There is no CPU fallback.")
-    h = C.CDLL(LIB_PATH)
+    h = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(h, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res

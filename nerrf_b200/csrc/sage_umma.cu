@@ -56,7 +56,11 @@ constexpr int NQ = 4;                  // sub-batch slots in a warp's ring; NQ-1
 // terms below 2^-24: fp32-equivalent.  NS = 2 with three products is ~1e-5 relative.
 template <int F, int NS>
 struct UmmaCfg {
+#ifdef NERRF_EXP_GW128                                            // experiment knob (scripts/exp_gather_warps.sh): fewer gather warps at F=128
+    static constexpr int GATHER_WARPS = (F == 32) ? 18 : (F == 128 ? NERRF_EXP_GW128 : 14);
+#else
     static constexpr int GATHER_WARPS = (F == 32) ? 18 : 14;  // F=32 leaves room for more rings (and needs more TLP)
+#endif
     static constexpr int THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;
     // F = 32 (quad-mode gather): a warp runs up to 3 units = ~7 tiles ahead of what it has consumed and holds a tile's edge
     // block from issue to completion, so the look-ahead is bounded by the number of edge-block stages, not by the rings
