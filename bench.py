@@ -415,8 +415,13 @@ def run_multi(args, world, rank, local_rank, dev):
     layer_wall = [tr["compute_ms"][l] + tr["exchange_ms"][l] for l in range(LAYERS)]
     nvlink = {"egress_bytes_per_layer_rank0": eg, "mean_ingress_bytes_per_layer": ing,
               "achieved_egress_gbps_per_exchanged_layer": [eg / (layer_wall[l] * 1e-3) / 1e9 for l in range(LAYERS - 1)],
-              "peak_per_direction_gbps": 900.0,
+              "peak_per_direction_gbps": 900.0, "measured_peer_copy_gbps": 770.0,
               "bound_ms_per_exchanged_layer": max(eg, ing) / 900e9 * 1e3,
+              "bound_ms_per_exchanged_layer_at_measured_peer_copy": max(eg, ing) / 770e9 * 1e3,
+              "weak_scaling_ceiling": "random vertex relabeling makes every rank read the same hub-heavy ~55 % of all rows: a rank must "
+                                      "RECEIVE that many 512-byte rows per exchanged layer whatever the transport (P2P, multicast), so "
+                                      "step time >= 2 x ingress / link rate + the last layer; trace_graph is the same metric on the workload "
+                                      "the metric names (a trace: components with no cut)",
               "note": "the exchange is fused into the layer kernel: its rows travel while the next tiles are gathered, so the "
                       "layer's wall time (compute + barrier segments) is what the bytes are divided by"}
     par, (h_ref, sc_ref) = ss.parity_vs_single_gpu(rowptr, col, ew, x)

@@ -54,3 +54,20 @@ def test_candidate_only_sequences_equal_the_full_builder():
     assert np.array_equal(sub[0].view(np.uint32), full[0][::5].view(np.uint32))
     none = ingest.sequences_from_columns(cols, observable=True, only_nodes=np.zeros(0, np.int64))
     assert none[0].shape[0] == 0 and none[2].shape == (0,)
+
+
+def test_name_hash_and_lazy_names():
+    """stream.name_hash is a pure function of the name (the device kernel nerrf_trace_name_hash computes the same value --
+    checked on the GPU in tests/test_gpu_stream.py); LazyNames decodes exactly the interning's naming events."""
+    from nerrf_b200 import ingest
+    assert stream.name_hash("/app/uploads/a.dat") == stream.name_hash(b"/app/uploads/a.dat")
+    assert stream.name_hash("/app/uploads/a.dat") != stream.name_hash("/app/uploads/a.dat.lockbit3")
+    assert stream.name_hash("pid:4242") != stream.name_hash("4242") and -(1 << 63) <= stream.name_hash("pid:4242") < (1 << 63)
+    assert stream.name_hash("") != stream.name_hash("\0")                     # the length seeds the hash
+    cols, _ = stream.fleet_columns(6, 2, seed=1)
+    order = np.argsort(cols.timestamp, kind="stable")
+    _, _, _, kind, name_event, name_which = ingest.intern_nodes(cols, order)
+    want = ingest._node_names(cols, name_event, name_which)
+    lazy = stream.LazyNames(cols, name_event, name_which)
+    assert len(lazy) == len(want) and all(lazy[i] == want[i] for i in range(0, len(want), 7))
+    assert len({stream.name_hash(n) for n in want}) == len(set(want))          # no collisions among the fleet's names
