@@ -189,6 +189,19 @@ int nerrf_mcts_search_host(const float* p, const float* size, const float* cost,
                            const uint32_t* root_state_host, int R, int D, int T, uint64_t seed,
                            float c, float lo, float inv_range, const float* ln_table_host,
                            int32_t* root_n_host, float* root_w_host, int32_t* num_nodes_host);
+/* plan(): validate-and-commit loop on the device (architecture.mdx:81-86 "sandbox validates, then apply"; the commit half of
+ * ai/planner/mcts.py plan()).  cand[n_cand] (device int32, ranked root children of a search) are scored as score(state + c)
+ * with the exact reward; the highest-ranked improving one is committed, the candidates that still improved stay in the list;
+ * repeated up to max_commits times.  allow_tentative != 0: if nothing improves at the first round the first candidate is
+ * committed anyway (spec-v1 lookahead).  state (device uint32 [32*NW]) is updated in place; actions_out / scores_out
+ * [max_commits] and n_out[2] = {commits made, candidates left} are device arrays.  Asynchronous on `stream`; one cooperative
+ * launch.  Decisions and scores are bit-identical to doing the loop with nerrf_reward_score on the host. */
+int nerrf_plan_commit_workspace_bytes(int n_cand_max, size_t* bytes);
+int nerrf_plan_commit(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
+                      uint32_t* state, const int32_t* cand, int n_cand, float cur, int max_commits,
+                      int allow_tentative, int32_t* actions_out, float* scores_out, int32_t* n_out,
+                      void* workspace, size_t workspace_bytes, nerrf_stream_t stream);
+
 /* HOST in / HOST out through a session: the device buffers and a stream live in the handle (create once for the
  * largest A / T / R; a search is then six small H2D copies, one launch and three D2H copies, no allocation).
  * A must have the same word count NW as A_max. */

@@ -51,6 +51,8 @@ SIGNATURES = {
                                     C.c_float, C.c_float, vp, vp, vp, vp, vp, C.c_size_t, vp]),
     "nerrf_mcts_search_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float,
                                          C.c_float, C.c_float, vp, vp, vp, vp]),
+    "nerrf_plan_commit_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "nerrf_plan_commit": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, vp]),
     "nerrf_mcts_session_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "nerrf_mcts_session_search_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint64,
                                                  C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]),

@@ -200,9 +200,49 @@ def ranked_children(root_n, root_w):
     return idx[order]
 
 
+class _DeviceCommit:
+    """Buffers + call wrapper of nerrf_plan_commit (the validate-and-commit loop of plan() in one cooperative launch)."""
+
+    def __init__(self, ctx: "SearchContext"):
+        self.ctx = ctx
+        dev = ctx.device
+        need = C.c_size_t()
+        L.check(L.lib().nerrf_plan_commit_workspace_bytes(4096, C.byref(need)), "nerrf_plan_commit_workspace_bytes")
+        self.ws = torch.empty(need.value, device=dev, dtype=torch.uint8)
+        self.ws_bytes = need.value
+        self.d_state = torch.empty(ctx.nw, device=dev, dtype=torch.int32)
+        self.d_cand = torch.empty(4096, device=dev, dtype=torch.int32)
+        # actions | scores | n_out | state in one buffer -> one D2H per search
+        self.cap = 4096
+        self.d_out = torch.empty(2 * self.cap + 2 + ctx.nw, device=dev, dtype=torch.int32)
+        self.h_out = torch.empty(2 * self.cap + 2 + ctx.nw, dtype=torch.int32).pin_memory()
+
+    def run(self, state: np.ndarray, cand: np.ndarray, cur: float, max_commits: int, allow_tentative: bool):
+        """-> (actions int list, scores float32 array, new state uint32 array, candidates left)."""
+        ctx = self.ctx
+        n = int(cand.shape[0])
+        max_commits = min(int(max_commits), self.cap)
+        with torch.cuda.device(ctx.device):
+            self.d_cand[:n].copy_(torch.from_numpy(np.ascontiguousarray(cand, np.int32)), non_blocking=False)
+            o = self.d_out
+            st = o[2 * self.cap + 2:]
+            st.copy_(torch.from_numpy(np.ascontiguousarray(state, np.uint32).view(np.int32)))
+            L.check(L.lib().nerrf_plan_commit(L.ptr(ctx.p), L.ptr(ctx.size), L.ptr(ctx.cost), L.ptr(ctx.guard), ctx.actions.A,
+                                              C.c_void_p(st.data_ptr()), L.ptr(self.d_cand), n, C.c_float(cur), max_commits,
+                                              int(bool(allow_tentative)), C.c_void_p(o.data_ptr()),
+                                              C.c_void_p(o.data_ptr() + 4 * self.cap), C.c_void_p(o.data_ptr() + 8 * self.cap),
+                                              L.ptr(self.ws), self.ws_bytes, L.current_stream_ptr()), "nerrf_plan_commit")
+            self.h_out.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h = self.h_out.numpy()
+        k = int(h[2 * self.cap])
+        return (h[:k].tolist(), h[self.cap:self.cap + k].view(np.float32).copy(), h[2 * self.cap + 2:].view(np.uint32).copy(),
+                int(h[2 * self.cap + 1]))
+
+
 def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096, depth: int = 50, seed: int = 0,
          c: float = math.sqrt(2.0), iterations: int = 64, device=None, commit_per_search: int = 1, merge=None,
-         lookahead: bool | None = None, patience: int = 8) -> Plan:
+         lookahead: bool | None = None, patience: int = 8, device_commit: bool = True) -> Plan:
     """Undo plan = repeated search / commit / re-root.  Each step the search ranks the root
     children; the candidates are then VALIDATED with the exact reward (one batched
     rewards.score call over all candidate next-states, mirroring the reference's "sandbox
@@ -218,13 +258,16 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
     costs downtime and only pays off through the reversions it makes durable -- so a step that no single action improves
     is not the end: the search's recommended child is committed TENTATIVELY, planning continues from there for at most
     `patience` steps below the best reward seen, and the plan is finally cut back to its best prefix (what the sandbox
-    would approve)."""
+    would approve).
+    device_commit (default): the validate-and-commit loop runs on the device in one launch per search (nerrf_plan_commit);
+    False keeps it as a host loop over rewards.score calls -- the same decisions bit for bit (tests compare the two)."""
     A = actions.A
     state = RW.empty_state(A)
     max_steps = A if max_steps is None else max_steps          # a plan may need every candidate; `depth` is the ROLLOUT horizon
     cur = float(RW.score(state[None, :], actions, device=device).cpu()[0])
     out = Plan([], [cur], [])
     ctx = SearchContext(actions, n_rollouts, depth, iterations, c, device)
+    dc = None
     step = 0
     lookahead = (actions.guard is not None) if lookahead is None else lookahead
     best_score, best_len = cur, 0
@@ -241,6 +284,18 @@ def plan(actions: Actions, max_steps: int | None = None, n_rollouts: int = 4096,
         if cand.size == 0:
             break
         committed = 0
+        if device_commit:
+            # the validate-and-commit loop below as ONE cooperative launch (nerrf_plan_commit): same decisions, same scores
+            dc = dc if dc is not None else _DeviceCommit(ctx)
+            acts, scs, state, _left = dc.run(state, cand, cur, min(commit_per_search, max_steps - len(out.actions)),
+                                             lookahead and len(out.actions) - best_len < patience)
+            for a_, s_ in zip(acts, scs.tolist()):
+                cur = float(s_)
+                out.actions.append(int(a_)); out.scores.append(cur)
+                committed += 1
+                if cur > best_score:
+                    best_score, best_len = cur, len(out.actions)
+            cand = cand[:0]
         while cand.size and committed < commit_per_search and len(out.actions) < max_steps:
             nxt = np.repeat(state[None, :], cand.size, axis=0)
             nxt[np.arange(cand.size), cand >> 5] |= (np.uint32(1) << (cand & 31).astype(np.uint32)).astype(np.uint32)

@@ -620,6 +620,119 @@ __global__ void __launch_bounds__(256) reward_score_kernel(const uint32_t* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------ plan(): validate and commit
+// The commit loop of ai.planner.mcts.plan ("sandbox validates, then apply", architecture.mdx:81-86) on the device.  After a tree
+// search the ranked root children are validated with the EXACT reward: repeatedly, every remaining candidate c is scored as
+// score(state + c) (the spec'd fixed-order fp32 sum: warp_score), the highest-ranked candidate that improves on the current
+// score is committed, and only candidates that still looked improving stay in the list -- up to max_commits times.  With
+// thousands of candidates and 64 commits per search this loop was ~90 % of the planner's wall time when every round was a
+// host round trip (states up, scores down).  Here: one cooperative launch, one grid barrier per round; every CTA keeps its
+// own copy of the state and of the candidate list and applies the (deterministic) round result to it, the round's scores /
+// flags travel through double-buffered global arrays.  Bit-identical decisions and scores to the host loop.
+struct CommitArgs {
+    const float *p, *size, *cost;
+    const int32_t* guard;
+    int A;
+    uint32_t* state;            // [32*NW] in: the current state, out: the state after the commits
+    const int32_t* cand;        // [n_cand] ranked candidates
+    int n_cand, max_commits, allow_tentative;
+    float cur;                  // exact score of `state`
+    float* sc_buf;              // [2][cap] scores of the round
+    int32_t* flag_buf;          // [2][cap] 1 = improves
+    int cap;
+    int32_t* actions_out;       // [max_commits]
+    float* scores_out;          // [max_commits]
+    int32_t* n_out;             // [0] commits made, [1] candidates left that still looked improving
+    unsigned* barrier;          // zero at launch
+};
+
+template <int NW>
+__global__ void __launch_bounds__(256) plan_commit_kernel(CommitArgs P) {
+    constexpr int NWORDS = 32 * NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TermsS terms = carve_terms<NW>(smem_raw);
+    int32_t* s_cand = reinterpret_cast<int32_t*>(smem_raw + terms_smem_bytes<NW>());          // [cap]
+    __shared__ uint32_t s_state[NWORDS];
+    __shared__ int s_first, s_cnt[8];
+    __shared__ float s_cur;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned bar_target = 0;
+    stage_terms<NW>(P.p, P.size, P.cost, P.guard, P.A, terms);
+    for (int i = tid; i < P.n_cand; i += 256) s_cand[i] = P.cand[i];
+    for (int k = tid; k < NWORDS; k += 256) s_state[k] = P.state[k];
+    if (tid == 0) s_cur = P.cur;
+    __syncthreads();
+    int n = P.n_cand, committed = 0;
+    const int gw = (int)blockIdx.x * 8 + warp, GW = (int)gridDim.x * 8;
+    for (int round = 0; n > 0 && committed < P.max_commits; ++round) {
+        float* sc = P.sc_buf + (size_t)(round & 1) * P.cap;
+        int32_t* fl = P.flag_buf + (size_t)(round & 1) * P.cap;
+        const float cur = s_cur;
+        for (int i = gw; i < n; i += GW) {                                // score(state + candidate i): one warp each
+            const int a = s_cand[i];
+            uint32_t w[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                w[k] = s_state[lane * NW + k];
+                if ((a >> 5) == lane * NW + k) w[k] |= 1u << (a & 31);
+            }
+            const float v = warp_score<NW>(w, terms, lane);
+            if (lane == 0) { sc[i] = v; fl[i] = v > cur ? 1 : 0; }
+        }
+        grid_barrier(P.barrier, bar_target);                              // the round's scores are visible to every CTA
+        // every CTA, redundantly: the first improving candidate; the improving candidates after it form the next list
+        if (tid == 0) s_first = 0x7fffffff;
+        __syncthreads();
+        int my_first = 0x7fffffff;
+        for (int i = tid; i < n; i += 256)
+            if (__ldcg(fl + i)) { my_first = i; break; }
+        if (my_first != 0x7fffffff) atomicMin(&s_first, my_first);
+        __syncthreads();
+        int first = s_first;
+        bool tentative = false;
+        if (first == 0x7fffffff) {
+            if (P.allow_tentative && committed == 0) { first = 0; tentative = true; }   // lookahead: the search's recommendation
+            else break;                                                   // (uniform: every thread read the same s_first)
+        }
+        // stable compaction of {i > first : fl[i]} into the front of s_cand (blocked: thread t owns a contiguous chunk)
+        const int chunk = (n + 255) / 256;
+        const int lo = tid * chunk, hi = min(lo + chunk, n);
+        int cnt = 0;
+        if (!tentative)
+            for (int i = max(lo, first + 1); i < hi; ++i) cnt += __ldcg(fl + i);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t_; }
+        if (lane == 31) s_cnt[warp] = inc;
+        const int a_first = s_cand[first];
+        const float new_cur = __ldcg(sc + first);
+        __syncthreads();                                                  // s_cnt complete; every thread has read s_cand[first]
+        int base = inc - cnt;
+        for (int w_ = 0; w_ < warp; ++w_) base += s_cnt[w_];
+        int total = 0;
+        for (int w_ = 0; w_ < 8; ++w_) total += s_cnt[w_];
+        int keep[16];                                                     // chunk <= 16 for cap <= 4096
+        int nk = 0;
+        if (!tentative)
+            for (int i = max(lo, first + 1); i < hi; ++i)
+                if (__ldcg(fl + i)) keep[nk++] = s_cand[i];
+        __syncthreads();                                                  // all reads of the old list are done
+        for (int j = 0; j < nk; ++j) s_cand[base + j] = keep[j];
+        if (tid == 0) {
+            s_state[a_first >> 5] |= 1u << (a_first & 31);
+            s_cur = new_cur;
+            if (blockIdx.x == 0) { P.actions_out[committed] = a_first; P.scores_out[committed] = new_cur; }
+        }
+        __syncthreads();
+        n = total;
+        committed += 1;
+    }
+    if (blockIdx.x == 0) {
+        for (int k = tid; k < NWORDS; k += 256) P.state[k] = s_state[k];
+        if (tid == 0) { P.n_out[0] = committed; P.n_out[1] = n; }
+    }
+}
+
 static int nw_for(int A) { return A <= 1024 ? 1 : (A <= 2048 ? 2 : 4); }
 
 static int mcts_grid_for(int R) {
@@ -819,4 +932,45 @@ extern "C" int nerrf_mcts_search_host(const float* p, const float* size, const f
                                         root_n_host, root_w_host, num_nodes_host);
     nerrf_mcts_session_destroy(s);
     return rc;
+}
+
+extern "C" int nerrf_plan_commit_workspace_bytes(int n_cand_max, size_t* bytes) {
+    NERRF_REQUIRE(bytes && n_cand_max >= 0 && n_cand_max <= 4096, "n_cand_max must be in 0..4096");
+    *bytes = (size_t)4096 * 16 + 256;
+    return NERRF_OK;
+}
+
+extern "C" int nerrf_plan_commit(const float* p, const float* size, const float* cost, const int32_t* guard, int A,
+                                 uint32_t* state, const int32_t* cand, int n_cand, float cur, int max_commits,
+                                 int allow_tentative, int32_t* actions_out, float* scores_out, int32_t* n_out,
+                                 void* workspace, size_t workspace_bytes, nerrf_stream_t stream) {
+    NERRF_REQUIRE(p && size && cost && state && actions_out && scores_out && n_out && workspace, "null pointer");
+    NERRF_REQUIRE(A >= 1 && A <= 4096, "number of actions must be in 1..4096 (got %d)", A);
+    NERRF_REQUIRE(n_cand >= 0 && n_cand <= 4096 && (n_cand == 0 || cand), "n_cand must be in 0..4096");
+    NERRF_REQUIRE(max_commits >= 0, "negative max_commits");
+    size_t need = 0;
+    nerrf_plan_commit_workspace_bytes(4096, &need);
+    NERRF_REQUIRE(workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0, "plan-commit workspace too small or misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    NERRF_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+    CommitArgs a;
+    a.p = p; a.size = size; a.cost = cost; a.guard = guard; a.A = A; a.state = state; a.cand = cand; a.n_cand = n_cand;
+    a.max_commits = max_commits; a.allow_tentative = allow_tentative; a.cur = cur; a.cap = 4096;
+    a.barrier = (unsigned*)ws;
+    a.sc_buf = (float*)(ws + 256); a.flag_buf = (int32_t*)(ws + 256 + (size_t)2 * 4096 * 4);
+    a.actions_out = actions_out; a.scores_out = scores_out; a.n_out = n_out;
+    const int NW = nw_for(A);
+    int grid = (n_cand + 7) / 8;
+    if (grid < 1) grid = 1;
+    if (grid > sm_count()) grid = sm_count();
+    void* kargs[] = {(void*)&a};
+    auto go = [&](auto kern, size_t smem) -> int {
+        NERRF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NERRF_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(256), kargs, smem, st));
+        return NERRF_OK;
+    };
+    if (NW == 1) return go(plan_commit_kernel<1>, terms_smem_bytes<1>() + 4096 * 4);
+    if (NW == 2) return go(plan_commit_kernel<2>, terms_smem_bytes<2>() + 4096 * 4);
+    return go(plan_commit_kernel<4>, terms_smem_bytes<4>() + 4096 * 4);
 }

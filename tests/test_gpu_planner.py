@@ -172,3 +172,27 @@ def test_host_session_reuses_buffers():
     assert np.array_equal(a.root_n, b.root_n) and np.array_equal(a.root_w, b.root_w)
     assert np.array_equal(c.root_n, d.root_n) and np.array_equal(c.root_w, d.root_w)
     sess.close()
+
+
+@pytest.mark.parametrize("A,cps,guards", [(300, 1, False), (1024, 64, False), (1500, 32, False), (4096, 64, False),
+                                          (200, 16, True), (1024, 64, True), (40, 1000, True)])
+def test_device_commit_equals_the_host_commit_loop(A, cps, guards):
+    """plan(): the validate-and-commit loop as one cooperative launch (nerrf_plan_commit) takes exactly the decisions of the
+    host loop over rewards.score calls -- same actions in the same order, same scores bit for bit, same truncation report --
+    for separable rewards (spec v0), guarded reversions with tentative lookahead commits (spec v1), NW = 1 / 2 / 4."""
+    rng = np.random.default_rng(A + cps)
+    act = _actions(A, seed=A)
+    if guards:
+        k = min(32, max(A // 8, 1))
+        guard = np.full(A, -1, np.int32)
+        guard[k:] = rng.integers(0, k, A - k)
+        cost = act.cost.copy(); cost[:k] = 10.0
+        size = act.size.copy(); size[:k] = 0.0
+        act = Actions(act.p, size, cost, guard=guard)
+    kw = dict(n_rollouts=256, depth=16, iterations=6, commit_per_search=cps, max_steps=min(A, 300), seed=3)
+    a = mcts.plan(act, device_commit=True, **kw)
+    b = mcts.plan(act, device_commit=False, **kw)
+    assert a.actions == b.actions, "committed actions differ"
+    assert np.array_equal(np.asarray(a.scores, np.float32).view(np.uint32), np.asarray(b.scores, np.float32).view(np.uint32))
+    assert a.truncated == b.truncated and a.remaining_candidates == b.remaining_candidates and len(a.searches) == len(b.searches)
+    assert len(a.actions) > 0
