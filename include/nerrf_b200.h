@@ -245,6 +245,22 @@ int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, const float* t
                           int64_t n_edges, int64_t n_nodes, float t_ref, float tau,
                           void* rowptr_out, int rowptr_is64, int32_t* col_out, float* ew_out,
                           void* workspace, int64_t workspace_bytes, nerrf_stream_t stream);
+/* The same, and also perm_out[i] (device uint32 [n_edges], may be NULL) = index in the INPUT edge list of the edge at CSR
+ * position i -- lets later stages (the per-file event sequences) go back from a CSR row to the events that made it. */
+int nerrf_graph_build_csr_ex(const int32_t* src, const int32_t* dst, const float* t, const float* conf,
+                             int64_t n_edges, int64_t n_nodes, float t_ref, float tau, void* rowptr_out,
+                             int rowptr_is64, int32_t* col_out, float* ew_out, uint32_t* perm_out, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+/* Per-file event sequences for lstm.forward on the device (architecture.mdx:55-59 "last 100 events per file"; spec =
+ * nerrf_b200/ingest.py sequences_core): for every candidate file node its last t_max events, oldest first, as
+ * seq_out [n_cand, t_max, 16] fp32 (zero padded) + len_out [n_cand].  Graph built from the window's events in time order
+ * with TWO edges per event (process -> file, file -> process: merge_renames mode), perm from nerrf_graph_build_csr_ex, order
+ * [n_window] = stored index of the window's events by rank; ts / event_slot / bytes / path_flags are the stored columns.
+ * All pointers device. */
+int nerrf_trace_sequences(const int64_t* cand_nodes, int n_cand, const void* rowptr, int rowptr_is64, const uint32_t* perm,
+                          const int64_t* order, const double* ts, const uint8_t* event_slot, const int64_t* bytes,
+                          const uint8_t* path_flags, double t0, double span, int t_max, float* seq_out,
+                          int32_t* len_out, void* stream);
 
 /* Per-node features on the device (rest of SURVEY.md 8f rank 1): event columns already mapped to node
  * ids (nerrf_trace_intern, events in time order) -> x [n_nodes, 32] in the layout GraphSAGE_T.forward

@@ -61,6 +61,9 @@ SIGNATURES = {
     "nerrf_lstm_forward": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp),
                                      C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, C.c_size_t, vp]),
     "nerrf_graph_csr_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "nerrf_graph_build_csr_ex": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, vp, C.c_int,
+                                           vp, vp, vp, vp, C.c_int64, vp]),
+    "nerrf_trace_sequences": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp]),
     "nerrf_graph_build_csr": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, vp, C.c_int,
                                         vp, vp, vp, C.c_int64, vp]),
     "nerrf_graph_node_features_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) csr_finish_kernel(const uint64_t* __restr
                                                           const int32_t* __restrict__ src, const float* __restrict__ t,
                                                           const float* __restrict__ conf, int64_t E, int64_t N, float t_ref,
                                                           float tau, RP* __restrict__ rowptr, int32_t* __restrict__ col,
-                                                          float* __restrict__ ew) {
+                                                          float* __restrict__ ew, uint32_t* __restrict__ perm_out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (int64_t wb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wb < E; wb += stride) {   // warp-uniform trip count
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) csr_finish_kernel(const uint64_t* __restr
         fill_rows(rowptr, d + 1, N, E, ok && i == E - 1, lane);             // rows after the last edge, and rowptr[N]
         if (ok) {
             const uint32_t e = perm[i];
+            if (perm_out) perm_out[i] = e;                               // CSR position -> index in the input edge list
             col[i] = __ldg(src + e);
             const float age = __fsub_rn(t_ref, __ldg(t + e));
             const float z = __fdiv_rn(-age, tau);
@@ -184,6 +185,52 @@ __global__ void __launch_bounds__(256) node_features_kernel(const NodeAcc* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-file event sequences for the LSTM, on the device (spec = nerrf_b200/ingest.py sequences_core; feature layout
+// pipeline.file_sequences): for candidate file node f the in-edges of row f ARE its events in time order (merge mode: every
+// event adds exactly one edge process -> file), perm maps a CSR position back to the input edge (= 2 * event rank), `order`
+// the rank to the stored event.  One warp per candidate; the last t_max events, oldest first.
+template <typename RP>
+__global__ void __launch_bounds__(256) trace_sequences_kernel(const int64_t* __restrict__ cand, int n_cand, const RP* __restrict__ rowptr,
+                                                               const uint32_t* __restrict__ perm, const int64_t* __restrict__ order,
+                                                               const double* __restrict__ ts, const uint8_t* __restrict__ slot,
+                                                               const int64_t* __restrict__ bytes, const uint8_t* __restrict__ pflags,
+                                                               double t0, double span, int t_max, float* __restrict__ seq,
+                                                               int32_t* __restrict__ len_out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= n_cand) return;
+    const int64_t f = cand[c];
+    const int64_t e0 = (int64_t)rowptr[f], e1 = (int64_t)rowptr[f + 1];
+    const int64_t deg = e1 - e0;
+    const int64_t start = deg > t_max ? deg - t_max : 0;
+    const int len = (int)(deg - start);
+    if (lane == 0) len_out[c] = len;
+    float* out = seq + (size_t)c * t_max * 16;
+    for (int k = lane; k < len; k += 32) {
+        const int64_t e = e0 + start + k;
+        const int64_t si = order[perm[e] >> 1];
+        const double t = ts[si];
+        double dt = 0.0;
+        if (k > 0) { const double tp = ts[order[perm[e - 1] >> 1]]; dt = fmin(t - tp, 10.0); }
+        float row[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) row[j] = 0.f;
+        const int sl = slot[si];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = (j == sl) ? 1.f : 0.f;
+        row[8] = (float)(log1p((double)bytes[si]) / 20.0);
+        row[9] = (float)dt;
+        row[10] = (float)((t - t0) / span);
+        const int pf = pflags[si];
+        row[11] = (pf & 1) ? 1.f : 0.f;
+        row[12] = (pf & 4) ? 1.f : 0.f;
+        float4* o = reinterpret_cast<float4*>(out + (size_t)k * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+    }
+}
+
 struct CsrWs {
     size_t keys_a, keys_b, vals_a, vals_b, bad, temp, total, temp_bytes;
 };
@@ -238,6 +285,14 @@ extern "C" int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, con
                                      int64_t n_edges, int64_t n_nodes, float t_ref, float tau, void* rowptr_out,
                                      int rowptr_is64, int32_t* col_out, float* ew_out, void* workspace,
                                      int64_t workspace_bytes, void* stream) {
+    return nerrf_graph_build_csr_ex(src, dst, t, conf, n_edges, n_nodes, t_ref, tau, rowptr_out, rowptr_is64, col_out, ew_out,
+                                    nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nerrf_graph_build_csr_ex(const int32_t* src, const int32_t* dst, const float* t, const float* conf,
+                                        int64_t n_edges, int64_t n_nodes, float t_ref, float tau, void* rowptr_out,
+                                        int rowptr_is64, int32_t* col_out, float* ew_out, uint32_t* perm_out, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
     NERRF_REQUIRE(n_edges >= 0 && n_edges < ((int64_t)1 << 32), "n_edges=%lld out of range [0, 2^32)", (long long)n_edges);
     NERRF_REQUIRE(n_nodes >= 1 && n_nodes < ((int64_t)1 << 31), "n_nodes=%lld out of range [1, 2^31)", (long long)n_nodes);
     NERRF_REQUIRE(rowptr_out != nullptr, "null rowptr_out");
@@ -290,10 +345,10 @@ extern "C" int nerrf_graph_build_csr(const int32_t* src, const int32_t* dst, con
     }
     if (rowptr_is64)
         csr_finish_kernel<int64_t><<<grid, 256, 0, st>>>(ks, vs, src, t, conf, n_edges, n_nodes, t_ref, tau,
-                                                         (int64_t*)rowptr_out, col_out, ew_out);
+                                                         (int64_t*)rowptr_out, col_out, ew_out, perm_out);
     else
         csr_finish_kernel<int32_t><<<grid, 256, 0, st>>>(ks, vs, src, t, conf, n_edges, n_nodes, t_ref, tau,
-                                                         (int32_t*)rowptr_out, col_out, ew_out);
+                                                         (int32_t*)rowptr_out, col_out, ew_out, perm_out);
     rc = launch_status("csr_finish_kernel");
     if (rc != NERRF_OK) return rc;
     // the vertex-id check is the one reason this call waits for the stream: out-of-range ids were clamped to row 0
@@ -342,4 +397,24 @@ extern "C" int nerrf_graph_node_features(const int32_t* node_p, const int32_t* n
     NERRF_CHECK_CUDA(cudaStreamSynchronize(st));
     NERRF_REQUIRE(h_bad == 0, "event columns hold a node id outside [0, n_nodes), a negative time or an event slot > 7");
     return NERRF_OK;
+}
+
+extern "C" int nerrf_trace_sequences(const int64_t* cand_nodes, int n_cand, const void* rowptr, int rowptr_is64, const uint32_t* perm,
+                                     const int64_t* order, const double* ts, const uint8_t* event_slot, const int64_t* bytes,
+                                     const uint8_t* path_flags, double t0, double span, int t_max, float* seq_out,
+                                     int32_t* len_out, void* stream) {
+    NERRF_REQUIRE(n_cand >= 0 && t_max >= 1, "bad sizes");
+    if (n_cand == 0) return NERRF_OK;
+    NERRF_REQUIRE(cand_nodes && rowptr && perm && order && ts && event_slot && bytes && path_flags && seq_out && len_out, "null pointer");
+    NERRF_REQUIRE(span > 0.0 && ((uintptr_t)seq_out & 15) == 0, "span must be positive, seq_out 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    NERRF_CHECK_CUDA(cudaMemsetAsync(seq_out, 0, (size_t)n_cand * t_max * 16 * sizeof(float), st));
+    const unsigned grid = (unsigned)((n_cand + 7) / 8);
+    if (rowptr_is64)
+        trace_sequences_kernel<int64_t><<<grid, 256, 0, st>>>(cand_nodes, n_cand, (const int64_t*)rowptr, perm, order, ts, event_slot, bytes,
+                                                              path_flags, t0, span, t_max, seq_out, len_out);
+    else
+        trace_sequences_kernel<int32_t><<<grid, 256, 0, st>>>(cand_nodes, n_cand, (const int32_t*)rowptr, perm, order, ts, event_slot, bytes,
+                                                              path_flags, t0, span, t_max, seq_out, len_out);
+    return launch_status("trace_sequences_kernel");
 }

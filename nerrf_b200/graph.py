@@ -57,7 +57,7 @@ def csr_from_edges(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU):
     return rowptr, src.astype(np.int32), ew
 
 
-def build_csr_device(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU, rowptr_dtype=None):
+def build_csr_device(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU, rowptr_dtype=None, return_perm=False):
     """Device half of the graph constructor (include/nerrf_b200.h nerrf_graph_build_csr): CUDA int32 src/dst and
     fp32 t/conf tensors -> (rowptr, col, ew) CUDA tensors, same contract as csr_from_edges (rowptr/col bit-exact,
     ew within the exp implementation's 2 ulp).  No CPU fallback."""
@@ -82,10 +82,13 @@ def build_csr_device(src, dst, t, conf, N, t_ref=WINDOW, tau=TAU, rowptr_dtype=N
         rowptr = torch.empty(int(N) + 1, dtype=rowptr_dtype, device=dev)
         col = torch.empty(E, dtype=torch.int32, device=dev)
         ew = torch.empty(E, dtype=torch.float32, device=dev)
-        _lib.check(h.nerrf_graph_build_csr(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(t), _lib.ptr(conf), E, int(N),
-                                           float(t_ref), float(tau), _lib.ptr(rowptr), int(rowptr_dtype == torch.int64),
-                                           _lib.ptr(col), _lib.ptr(ew), _lib.ptr(ws), ws.numel(),
-                                           _lib.current_stream_ptr()), "nerrf_graph_build_csr")
+        perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev) if return_perm else None     # uint32 bit patterns
+        _lib.check(h.nerrf_graph_build_csr_ex(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(t), _lib.ptr(conf), E, int(N),
+                                              float(t_ref), float(tau), _lib.ptr(rowptr), int(rowptr_dtype == torch.int64),
+                                              _lib.ptr(col), _lib.ptr(ew), _lib.ptr(perm), _lib.ptr(ws), ws.numel(),
+                                              _lib.current_stream_ptr()), "nerrf_graph_build_csr_ex")
+    if return_perm:
+        return rowptr, col, ew, perm
     return rowptr, col, ew
 
 

@@ -102,6 +102,8 @@ def _sage_scores(g_dev, model, ctx):
 
 
 def _lstm_probs(seq_model, seq_sel, len_sel, dev, ctx):
+    if torch.is_tensor(seq_sel):                                       # built on the device (stream.DeviceStream.sequences_device)
+        return seq_model(seq_sel.to(dev), len_sel.to(dev))
     if ctx is None or ctx.world == 1 or seq_sel.shape[0] < ctx.world:
         return seq_model(torch.from_numpy(seq_sel).to(dev), torch.from_numpy(len_sel).to(dev))
     import torch.distributed as dist
@@ -183,10 +185,13 @@ def run(g: G.TemporalGraph, seq, lengths, seq_nodes, model: GraphSAGE_T, seq_mod
     t0 = time.perf_counter()
     if callable(seq):
         want = candidates.cpu().numpy()
-        sq, ln, have = seq(want)                                       # sequences of the candidates only (sorted by node id)
-        pos = np.searchsorted(have, want)
-        assert have.shape[0] == want.shape[0] and np.array_equal(have[pos], want), "every candidate file has events"
-        seq_sel, len_sel = sq[pos], ln[pos]
+        sq, ln, have = seq(want)                                       # sequences of the candidates only
+        if have is None:                                               # already in candidate order (device builder: CUDA tensors)
+            seq_sel, len_sel = sq, ln
+        else:                                                          # sorted by node id (host builder)
+            pos = np.searchsorted(have, want)
+            assert have.shape[0] == want.shape[0] and np.array_equal(have[pos], want), "every candidate file has events"
+            seq_sel, len_sel = sq[pos], ln[pos]
         tm["sequences"] = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter()
     else:

@@ -187,6 +187,7 @@ class DeviceStream:
         if self.merge:                                        # the renamed twin is the same node: its .lockbit bit counts
             pf = pf | (ingest.path_flags_of(goff, gdata) & np.uint8(1))
         self.d_pf = up(pf, np.uint8)
+        self.d_pf_raw = up(cols.path_flags, np.uint8)         # the sequences use the event's own path flags
         self.cap = max((2 if self.merge else 3) * n, 1)
         self.node_p = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.node_f = torch.empty_like(self.node_p); self.node_g = torch.empty_like(self.node_p)
@@ -242,8 +243,8 @@ class DeviceStream:
             keep = torch.stack([torch.ones_like(P, dtype=torch.bool)] * 2 + [Gn >= 0] * 2, 1).reshape(-1)
             src = torch.stack([P, F, F, Gn], 1).reshape(-1)[keep]; dst = torch.stack([F, P, Gn, F], 1).reshape(-1)[keep]
             te = tt.repeat_interleave(4)[keep]
-        rowptr, col, ew = G.build_csr_device(src.contiguous(), dst.contiguous(), te.contiguous(), torch.ones_like(te), N,
-                                             t_ref=float(span), tau=G.TAU)
+        rowptr, col, ew, perm = G.build_csr_device(src.contiguous(), dst.contiguous(), te.contiguous(), torch.ones_like(te), N,
+                                                   t_ref=float(span), tau=G.TAU, return_perm=True)
         lab = label
         if self.observable:                                         # the kernel saw the folded slots: labels come from the annotations
             raw = self.d_raw_slot[sel]
@@ -257,8 +258,32 @@ class DeviceStream:
         meta = {"kind": "trace", "names": LazyNames(self.cols, self.name_event[:N].cpu().numpy(), self.name_which[:N].cpu().numpy()),
                 "node_kind": kind_d.cpu().numpy().astype(np.int64), "t0": t0, "span": span, "merge_renames": self.merge,
                 "label": lab.cpu().numpy().astype(np.int64), "size_mb": size_mb.cpu().numpy(), "device": str(self.dev),
-                "name_hash": nh, "events": nw, "window_ranks": (lo, hi)}
+                "name_hash": nh, "events": nw, "window_ranks": (lo, hi), "perm": perm if Gn is None else None}
         return G.TemporalGraph(rowptr, col, ew, x, meta)
+
+    def sequences_device(self, g: G.TemporalGraph, only_nodes):
+        """LSTM sequences of the given file nodes of window graph `g`, built ON THE DEVICE (nerrf_trace_sequences) from the
+        resident columns and the graph's own CSR rows: -> (seq fp32 [A, T_MAX, 16], lengths int32 [A]) CUDA tensors in the
+        order of `only_nodes`.  Needs the two-edges-per-event graph of merge mode (g.meta['perm'])."""
+        import ctypes as C
+        from . import _lib
+        from .ai.models import lstm
+        torch = self.torch
+        perm = g.meta.get("perm")
+        if perm is None:
+            raise _lib.NerrfError("sequences_device needs a merge-mode window graph (two edges per event)")
+        lo, hi = g.meta["window_ranks"]
+        cand = torch.as_tensor(np.asarray(only_nodes, np.int64)).to(self.dev)
+        A = int(cand.shape[0])
+        seq = torch.empty(A, lstm.T_MAX, lstm.D_IN, dtype=torch.float32, device=self.dev)
+        ln = torch.empty(A, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().nerrf_trace_sequences(_lib.ptr(cand), A, _lib.ptr(g.rowptr), int(g.rowptr.dtype == torch.int64),
+                                                        _lib.ptr(perm), _lib.ptr(self.d_order[lo:hi]), _lib.ptr(self.d_ts),
+                                                        _lib.ptr(self.d_slot), _lib.ptr(self.d_bytes), _lib.ptr(self.d_pf_raw),
+                                                        float(g.meta["t0"]), float(g.meta["span"]), lstm.T_MAX, _lib.ptr(seq),
+                                                        _lib.ptr(ln), _lib.current_stream_ptr()), "nerrf_trace_sequences")
+        return seq, ln
 
     def sequences(self, g: G.TemporalGraph, only_nodes):
         """LSTM sequences of the given file nodes of window graph `g` (ingest.sequences_core on the window's events)."""
@@ -372,6 +397,9 @@ class StreamingPlanner:
 
             # LSTM sequences are built lazily, for the top-A candidates only (a window holds ~10^6 file nodes)
             def seq(cand, g=g):
+                if lead and not multi:                      # built on the device from the resident columns, in candidate order
+                    sq_d, ln_d = ds.sequences_device(g, cand)
+                    return sq_d, ln_d, None
                 if lead:
                     sq, ln, have = ds.sequences(g, cand)
                 if multi:

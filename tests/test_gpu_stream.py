@@ -69,3 +69,10 @@ def test_device_stream_window_equals_the_columnar_constructor():
         sq, ln, have = ds.sequences(g, files)
         sq2, ln2, have2 = ingest.sequences_from_columns(w, observable=True, only_nodes=files)
         assert np.array_equal(have, have2) and np.array_equal(ln, ln2) and np.array_equal(sq, sq2)
+        # the same sequences built on the device from the resident columns (any candidate order, duplicates allowed)
+        pick_f = np.random.default_rng(1).permutation(have)[:200]
+        sq_d, ln_d = ds.sequences_device(g, pick_f)
+        pos = np.searchsorted(have, pick_f)
+        assert np.array_equal(ln_d.cpu().numpy(), ln[pos])
+        assert np.allclose(sq_d.cpu().numpy(), sq[pos], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(sq_d.cpu().numpy()[:, :, :8], sq[pos][:, :, :8])           # one-hot slots exactly
