@@ -202,6 +202,8 @@ class DeviceStream:
         self._ws_bytes = need.value
 
     def span(self):
+        if self.n == 0:
+            return 0.0, 0.0
         return float(self.ts_sorted[0]), float(self.ts_sorted[-1])
 
     def window_graph(self, t_lo: float, t_hi: float, window_s: float):

@@ -76,3 +76,10 @@ def test_device_stream_window_equals_the_columnar_constructor():
         assert np.array_equal(ln_d.cpu().numpy(), ln[pos])
         assert np.allclose(sq_d.cpu().numpy(), sq[pos], rtol=1e-6, atol=1e-7)
         assert np.array_equal(sq_d.cpu().numpy()[:, :, :8], sq[pos][:, :, :8])           # one-hot slots exactly
+
+
+def test_empty_stream_is_a_no_op(models):
+    from nerrf_b200 import ingest
+    model, scorer = models
+    sp = stream.StreamingPlanner(model, scorer)
+    assert sp.run(ingest.decode_event_batch(b"")) == [] and not sp.reverted
