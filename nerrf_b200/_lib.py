@@ -90,10 +90,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("NERRF_LIB", LIB_PATH)                # experiment builds of the same library (scripts/)
+    path = os.environ.get("NERRF_LIB") or LIB_PATH                 # experiment builds of the same library (scripts/)
     if not os.path.exists(path):
         raise NerrfError(
-            f"{LIB_PATH} not found: build it with `python -m nerrf_b200.build` "
+            f"{path} not found: build it with `python -m nerrf_b200.build` "
             "(nvcc, sm_100a).  There is no CPU fallback.")
     h = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
