@@ -19,9 +19,6 @@ in tests (with the oracle as the layer) and on GPUs under NCCL (with the CUDA ke
 """
 from __future__ import annotations
 
-import json
-import os
-import time
 
 import numpy as np
 import torch
